@@ -50,6 +50,7 @@ enum {
   MJP_INST_LOGBUF_EMPTY = 4,  /* push-log returned nil (util/log.clj:95): reference dies */
   MJP_INST_TICK_OVERFLOW= 5,  /* device-only: more same-clock messages than the staging
                                  area holds; instance stopped, statistics invalid     */
+  MJP_INST_ITER_LIMIT   = 6,  /* device-only: watchdog on loop iterations tripped        */
   MJP_INST_NOT_RUN      = 255
 };
 
@@ -133,8 +134,8 @@ typedef struct mjp_rng_spec {
 
 /* ---- per-instance results: the content of the log-steady ref ------------------- */
 /* Caller-allocated, instance-fastest SoA.  L = sum_b (N[b]+1) occupancy levels;
- * level n of buffer b is row  (sum_{c<b} (N[c]+1)) + n.  Any pointer except
- * `status` may be NULL (not wanted).                                         */
+ * level n of buffer b is row  (sum_{c<b} (N[c]+1)) + n.  Any pointer may be
+ * NULL (plane not wanted).                                                   */
 typedef struct mjp_stats_out {
   int64_t  *njobs;          /* [n]     :njobs          util/log.clj:217        */
   double   *residence_sum;  /* [n]     :residence-sum  util/log.clj:216        */

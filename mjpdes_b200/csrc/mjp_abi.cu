@@ -1,0 +1,444 @@
+// mjp_abi.cu -- host side of the C ABI declared in include/mjpdes_b200.h.
+//
+// The handle owns every device buffer, a stream and two timing events; the
+// caller owns every host buffer.  No call throws or aborts: errors come back
+// as MJP_ERR_* with text in mjp_last_error().
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mjpdes_b200.h"
+#include "mjp_line_kernel.cuh"
+#include "mjp_plan.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&ptr, bytes ? bytes : 16);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+}  // namespace
+
+struct mjp_handle {
+  int device = 0;
+  int flags = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  // uploaded line
+  bool uploaded = false, launched = false, sweep = false;
+  mjp::KParams kp{};
+  std::vector<int32_t> Ncap;
+  // device buffers
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage;
+  // out-plane offsets inside d_out (bytes)
+  size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
+         o_status = 0, out_bytes = 0, zero_bytes = 0;
+  int agg_blocks = 0;
+  bool want_log = false;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  int block_threads = 0;
+  size_t smem_bytes = 0;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
+      return e__ == cudaErrorMemoryAllocation ? MJP_ERR_NOMEM : MJP_ERR_CUDA;                      \
+    }                                                                                              \
+  } while (0)
+
+static int fail(mjp_handle *h, int code, const char *msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+namespace mjp {
+// SCADA capture path (filled in by the log kernel)
+static int reserve_log(mjp_handle *h, uint64_t capacity) {
+  (void)capacity;
+  return fail(h, MJP_ERR_UNSUPPORTED, "SCADA log capture is not available in this build");
+}
+static int launch_log_path(mjp_handle *h, bool, bool, int *) {
+  return fail(h, MJP_ERR_UNSUPPORTED, "SCADA log capture is not available in this build");
+}
+}  // namespace mjp
+
+/* the checks of core.clj:75-121 (clojure.spec) that concern the loop, plus the kernel's own limits */
+static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
+  if (!L) return fail(h, MJP_ERR_INVALID, "line descriptor is NULL");
+  if (n_inst == 0) return fail(h, MJP_ERR_INVALID, "n_inst must be >= 1");
+  if (n_inst > (1ull << 32)) return fail(h, MJP_ERR_UNSUPPORTED, "more than 2^32 instances per call");
+  if (L->M < 2) return fail(h, MJP_ERR_INVALID, ":line needs at least two machines and a buffer (core.clj:120)");
+  if (L->M > MJP_MAX_MACHINES) return fail(h, MJP_ERR_UNSUPPORTED, "more than 64 machines");
+  if (L->K < 1) return fail(h, MJP_ERR_INVALID, ":jobmix is empty (core.clj:117)");
+  if (L->K > MJP_MAX_JOBTYPES) return fail(h, MJP_ERR_UNSUPPORTED, "more than 255 job types");
+  if (!L->lambda || !L->mu || !L->W || !L->discipline || !L->N || !L->portion || !L->w)
+    return fail(h, MJP_ERR_INVALID, "a required array of the line descriptor is NULL");
+  for (int i = 0; i < L->M; ++i) {
+    if (!(L->lambda[i] >= 0.0)) return fail(h, MJP_ERR_INVALID, ":lambda must be non-negative (core.clj:89)");
+    if (!(L->mu[i] > 0.0)) return fail(h, MJP_ERR_INVALID, ":mu must be positive (core.clj:88)");
+    if (!(L->W[i] > 0.0)) return fail(h, MJP_ERR_INVALID, ":W must be positive (core.clj:87)");
+    if (L->discipline[i] > 1) return fail(h, MJP_ERR_INVALID, ":discipline must be :BAS or :BBS (core.clj:91)");
+  }
+  for (int b = 0; b < L->M - 1; ++b) {
+    if (L->N[b] < 1) return fail(h, MJP_ERR_INVALID, ":N must be a positive integer (core.clj:95)");
+    if (L->N[b] > 254) return fail(h, MJP_ERR_UNSUPPORTED, "buffer capacity above 254");
+  }
+  for (int k = 0; k < L->K; ++k)
+    if (!(L->portion[k] > 0.0)) return fail(h, MJP_ERR_INVALID, ":portion must be positive (core.clj:109)");
+  for (int q = 0; q < L->K * L->M; ++q)
+    if (!(L->w[q] > 0.0)) return fail(h, MJP_ERR_INVALID, ":w values must be positive (core.clj:108)");
+  if (!(L->warm_up >= 0.0)) return fail(h, MJP_ERR_INVALID, ":warm-up-time must be non-negative (core.clj:104)");
+  if (!(L->run_to > 0.0)) return fail(h, MJP_ERR_INVALID, ":run-to-time must be positive (core.clj:105)");
+  if (L->N_inst)
+    for (int b = 0; b < L->M - 1; ++b)
+      for (uint64_t g = 0; g < n_inst; ++g) {
+        const int v = L->N_inst[(size_t)b * n_inst + g];
+        if (v < 1 || v > L->N[b]) return fail(h, MJP_ERR_INVALID, "N_inst value outside 1..N[b]");
+      }
+  const uint64_t nm = n_inst * (uint64_t)L->M, nkm = n_inst * (uint64_t)L->M * (uint64_t)L->K;
+  if (L->lambda_inst) for (uint64_t q = 0; q < nm; ++q) if (!(L->lambda_inst[q] >= 0.0)) return fail(h, MJP_ERR_INVALID, "lambda_inst must be non-negative");
+  if (L->mu_inst) for (uint64_t q = 0; q < nm; ++q) if (!(L->mu_inst[q] > 0.0)) return fail(h, MJP_ERR_INVALID, "mu_inst must be positive");
+  if (L->W_inst) for (uint64_t q = 0; q < nm; ++q) if (!(L->W_inst[q] > 0.0)) return fail(h, MJP_ERR_INVALID, "W_inst must be positive");
+  if (L->w_inst) for (uint64_t q = 0; q < nkm; ++q) if (!(L->w_inst[q] > 0.0)) return fail(h, MJP_ERR_INVALID, "w_inst must be positive");
+  return MJP_OK;
+}
+
+template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP>
+static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int threads, size_t smem, cudaStream_t st) {
+  auto k = mjp::mjp_line_kernel<MaskT, REPLAY, HASH, SWEEP>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<blocks, threads, smem, st>>>(kp);
+  return cudaGetLastError();
+}
+
+template <typename MaskT>
+static cudaError_t launch_mask(bool replay, bool hash, bool sweep, const mjp::KParams &kp, int blocks, int threads,
+                               size_t smem, cudaStream_t st) {
+  const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
+  switch (v) {
+    case 0: return launch_variant<MaskT, false, false, false>(kp, blocks, threads, smem, st);
+    case 1: return launch_variant<MaskT, false, false, true>(kp, blocks, threads, smem, st);
+    case 2: return launch_variant<MaskT, false, true, false>(kp, blocks, threads, smem, st);
+    case 3: return launch_variant<MaskT, false, true, true>(kp, blocks, threads, smem, st);
+    case 4: return launch_variant<MaskT, true, false, false>(kp, blocks, threads, smem, st);
+    case 5: return launch_variant<MaskT, true, false, true>(kp, blocks, threads, smem, st);
+    case 6: return launch_variant<MaskT, true, true, false>(kp, blocks, threads, smem, st);
+    default: return launch_variant<MaskT, true, true, true>(kp, blocks, threads, smem, st);
+  }
+}
+
+extern "C" {
+
+int mjp_abi_version(void) { return MJP_ABI_VERSION; }
+
+int mjp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int mjp_aggregate_len(int32_t M) { return 1 + 2 * (3 * M + 1); }
+
+int mjp_create(const mjp_config *cfg, mjp_handle **out) {
+  if (!out) return MJP_ERR_INVALID;
+  *out = nullptr;
+  mjp_handle *h = new (std::nothrow) mjp_handle();
+  if (!h) return MJP_ERR_NOMEM;
+  h->device = cfg ? cfg->device : 0;
+  h->flags = cfg ? cfg->flags : 0;
+  cudaError_t e = cudaSetDevice(h->device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, h->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("mjp_create: ") + cudaGetErrorString(e);
+    delete h;
+    return MJP_ERR_CUDA;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return MJP_OK;
+}
+
+void mjp_destroy(mjp_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
+                    &h->d_logcur, &h->d_stage})
+    b->release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *mjp_last_error(const mjp_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
+  if (!h) return MJP_ERR_INVALID;
+  h->uploaded = false; h->launched = false;
+  int rc = validate(h, L, n_inst);
+  if (rc != MJP_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  const int M = L->M, K = L->K;
+  mjp::LinePlan pl = mjp::build_plan(L, n_inst);
+  mjp::KParams &kp = h->kp;
+  kp = pl.kp;
+  const int R = kp.R, levels = kp.L;
+  h->Ncap.assign(L->N, L->N + (M - 1));
+
+  // ---- constants: lam mu W w dur thr | N lvl ----
+  const size_t dbytes = pl.cd.size() * sizeof(double), ibytes = pl.ci.size() * sizeof(int32_t);
+  CK(h->d_const.reserve(dbytes + ibytes));
+  CK(cudaMemcpyAsync(h->d_const.ptr, pl.cd.data(), dbytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync((char *)h->d_const.ptr + dbytes, pl.ci.data(), ibytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // pl is stack-owned
+  const double *dc = h->d_const.as<double>();
+  kp.lam = dc + pl.off_lam(); kp.mu = dc + pl.off_mu(); kp.W = dc + pl.off_W(); kp.w = dc + pl.off_w();
+  kp.dur = dc + pl.off_dur(); kp.thr = dc + pl.off_thr();
+  kp.N = reinterpret_cast<const int32_t *>((const char *)h->d_const.ptr + dbytes);
+  kp.lvl = kp.N + (M - 1);
+
+  // ---- per-instance planes ----
+  const size_t pM = align_up(n_inst * M * sizeof(double), 256), pKM = align_up(n_inst * (size_t)K * M * sizeof(double), 256);
+  const size_t pN = align_up(n_inst * (size_t)(M - 1) * sizeof(int32_t), 256);
+  size_t need = (L->lambda_inst ? pM : 0) + (L->mu_inst ? pM : 0) + (L->W_inst ? pM : 0) + (L->w_inst ? pKM : 0) +
+                (L->N_inst ? pN : 0);
+  h->sweep = need != 0;
+  if (need) {
+    CK(h->d_planes.reserve(need));
+    char *base = (char *)h->d_planes.ptr;
+    size_t off = 0;
+    auto put = [&](const void *src, size_t bytes, size_t padded) -> const void * {
+      if (!src) return nullptr;
+      void *dst = base + off;
+      cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+      off += padded;
+      return dst;
+    };
+    kp.lam_i = (const double *)put(L->lambda_inst, n_inst * M * sizeof(double), pM);
+    kp.mu_i = (const double *)put(L->mu_inst, n_inst * M * sizeof(double), pM);
+    kp.W_i = (const double *)put(L->W_inst, n_inst * M * sizeof(double), pM);
+    kp.w_i = (const double *)put(L->w_inst, n_inst * (size_t)K * M * sizeof(double), pKM);
+    kp.N_i = (const int32_t *)put(L->N_inst, n_inst * (size_t)(M - 1) * sizeof(int32_t), pN);
+    CK(cudaGetLastError());
+  }
+
+  // ---- outputs: [blocked | starved | occ] are accumulated into and must be zeroed per launch ----
+  const size_t n = n_inst;
+  size_t off = 0;
+  auto plane = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  h->o_blk = plane(n * M * 8); h->o_stv = plane(n * M * 8); h->o_occ = plane(n * (size_t)levels * 8);
+  h->zero_bytes = off;
+  h->o_njobs = plane(n * 8); h->o_res = plane(n * 8); h->o_clk = plane(n * 8); h->o_cur = plane(n * 8);
+  h->o_nev = plane(n * 8); h->o_hash = plane(n * 8); h->o_status = plane(n);
+  h->out_bytes = off;
+  CK(h->d_out.reserve(off));
+  char *ob = (char *)h->d_out.ptr;
+  kp.blocked = (double *)(ob + h->o_blk); kp.starved = (double *)(ob + h->o_stv); kp.occ = (double *)(ob + h->o_occ);
+  kp.njobs = (int64_t *)(ob + h->o_njobs); kp.residence = (double *)(ob + h->o_res);
+  kp.final_clock = (double *)(ob + h->o_clk); kp.curjob = (int64_t *)(ob + h->o_cur);
+  kp.n_events = (uint64_t *)(ob + h->o_nev); kp.hash = (uint64_t *)(ob + h->o_hash);
+  kp.status = (uint8_t *)(ob + h->o_status);
+  CK(h->d_scratch.reserve(n * (size_t)R * 8));
+  kp.enters = h->d_scratch.as<double>();
+
+  // ---- launch shape ----
+  const size_t per_thread = pl.per_thread_bytes;
+  int threads = 0;
+  for (int t : {128, 64, 32}) {
+    if ((size_t)kp.const_bytes + per_thread * t <= h->smem_optin) { threads = t; break; }
+  }
+  if (!threads) return fail(h, MJP_ERR_UNSUPPORTED, "line state does not fit in shared memory (M, sum N too large)");
+  h->block_threads = threads;
+  h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
+
+  // aggregate scratch
+  h->agg_blocks = h->sm_count > 0 ? h->sm_count : 148;
+  const int len = mjp_aggregate_len(M);
+  CK(h->d_partials.reserve((size_t)h->agg_blocks * len * 8));
+  CK(h->d_agg.reserve((size_t)len * 8));
+  CK(h->d_logcur.reserve(16));
+  CK(cudaStreamSynchronize(h->stream));
+  h->uploaded = true;
+  return MJP_OK;
+}
+
+int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
+  if (!h) return MJP_ERR_INVALID;
+  if (!h->uploaded) return fail(h, MJP_ERR_INVALID, "mjp_launch before mjp_upload");
+  if (!rng || (rng->mode != MJP_RNG_COUNTER && rng->mode != MJP_RNG_REPLAY))
+    return fail(h, MJP_ERR_INVALID, "bad mjp_rng_spec");
+  CK(cudaSetDevice(h->device));
+  mjp::KParams &kp = h->kp;
+  kp.seed = rng->seed;
+  kp.first_id = rng->first_instance_id;
+  h->want_log = want_log && kp.log_on;
+  int launches = 0;
+  CK(cudaMemsetAsync(h->d_out.ptr, 0, h->zero_bytes, h->stream));
+  CK(cudaMemsetAsync((char *)h->d_out.ptr + h->o_status, MJP_INST_NOT_RUN, kp.n_inst, h->stream));
+  CK(cudaMemsetAsync(h->d_logcur.ptr, 0, 16, h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  const bool replay = rng->mode == MJP_RNG_REPLAY, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
+  if (h->want_log) {
+    int rc = mjp::launch_log_path(h, replay, hash, &launches);
+    if (rc != MJP_OK) return rc;
+  } else {
+    const int threads = h->block_threads;
+    const int blocks = (int)((kp.n_inst + threads - 1) / threads);
+    cudaError_t e = (kp.M <= 32)
+        ? launch_mask<uint32_t>(replay, hash, h->sweep, kp, blocks, threads, h->smem_bytes, h->stream)
+        : launch_mask<uint64_t>(replay, hash, h->sweep, kp, blocks, threads, h->smem_bytes, h->stream);
+    CK(e);
+    launches++;
+  }
+  {
+    const int n_metrics = 3 * kp.M + 1;
+    mjp::mjp_aggregate_partial<<<h->agg_blocks, 256, 2 * 256 * sizeof(double), h->stream>>>(
+        kp, h->d_partials.as<double>(), n_metrics);
+    CK(cudaGetLastError());
+    const int len = 1 + 2 * n_metrics;
+    mjp::mjp_aggregate_final<<<(len + 127) / 128, 128, 0, h->stream>>>(h->d_partials.as<double>(), h->agg_blocks, len,
+                                                                      h->d_agg.as<double>());
+    CK(cudaGetLastError());
+    launches += 2;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->last_launches = launches;
+  h->launched = true;
+  return MJP_OK;
+}
+
+int mjp_sync(mjp_handle *h) {
+  if (!h) return MJP_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->launched) CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return MJP_OK;
+}
+
+int mjp_download(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log) {
+  if (!h) return MJP_ERR_INVALID;
+  if (!h->launched) return fail(h, MJP_ERR_INVALID, "mjp_download before mjp_launch");
+  CK(cudaSetDevice(h->device));
+  const mjp::KParams &kp = h->kp;
+  const size_t n = kp.n_inst;
+  const char *ob = (const char *)h->d_out.ptr;
+  auto get = [&](void *dst, size_t o, size_t bytes) {
+    if (dst) cudaMemcpyAsync(dst, ob + o, bytes, cudaMemcpyDeviceToHost, h->stream);
+  };
+  if (s) {
+    get(s->njobs, h->o_njobs, n * 8); get(s->residence_sum, h->o_res, n * 8);
+    get(s->blocked_time, h->o_blk, n * kp.M * 8); get(s->starved_time, h->o_stv, n * kp.M * 8);
+    get(s->occ_time, h->o_occ, n * (size_t)kp.L * 8); get(s->final_clock, h->o_clk, n * 8);
+    get(s->current_job, h->o_cur, n * 8); get(s->n_events, h->o_nev, n * 8);
+    if (s->event_hash) {
+      if (h->flags & MJP_CFG_EVENT_HASH) get(s->event_hash, h->o_hash, n * 8);
+      else std::memset(s->event_hash, 0, n * 8);
+    }
+    get(s->status, h->o_status, n);
+    if (s->aggregate)
+      cudaMemcpyAsync(s->aggregate, h->d_agg.ptr, (size_t)mjp_aggregate_len(kp.M) * 8, cudaMemcpyDeviceToHost, h->stream);
+  }
+  int rc = MJP_OK;
+  if (log) {
+    log->count = 0; log->dropped = 0;
+    if (h->want_log) {
+      unsigned long long cur[2] = {0, 0};
+      CK(cudaMemcpyAsync(cur, h->d_logcur.ptr, 16, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      uint64_t have = cur[0] < kp.log_capacity ? cur[0] : kp.log_capacity;
+      uint64_t dropped = cur[1] + (cur[0] > kp.log_capacity ? cur[0] - kp.log_capacity : 0);
+      uint64_t take = have < log->capacity ? have : log->capacity;
+      if (take && log->records)
+        CK(cudaMemcpyAsync(log->records, h->d_log.ptr, take * sizeof(mjp_log_record), cudaMemcpyDeviceToHost, h->stream));
+      log->count = take;
+      log->dropped = dropped + (have - take);
+      if (log->dropped) rc = MJP_LOG_TRUNCATED;
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+
+int mjp_run(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst, const mjp_rng_spec *rng,
+            mjp_stats_out *stats, mjp_log_out *log) {
+  int rc = mjp_upload(h, line, n_inst);
+  if (rc != MJP_OK) return rc;
+  if (log && line->log) {
+    rc = mjp::reserve_log(h, log->capacity);
+    if (rc != MJP_OK) return rc;
+  }
+  rc = mjp_launch(h, rng, log != nullptr);
+  if (rc != MJP_OK) return rc;
+  rc = mjp_sync(h);
+  if (rc != MJP_OK) return rc;
+  return mjp_download(h, stats, log);
+}
+
+int mjp_last_kernel_ms(mjp_handle *h, float *ms) {
+  if (!h || !ms) return MJP_ERR_INVALID;
+  *ms = h->last_ms;
+  return MJP_OK;
+}
+
+int mjp_last_launch_count(mjp_handle *h, int *n) {
+  if (!h || !n) return MJP_ERR_INVALID;
+  *n = h->last_launches;
+  return MJP_OK;
+}
+
+int mjp_probe_end_time(mjp_handle *h, const uint8_t *kinds, const double *times, int32_t n_events, double clock,
+                       double dur, double *out) {
+  if (!h || !kinds || !times || !out || n_events < 1) return MJP_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevBuf buf;
+  const size_t tb = align_up((size_t)n_events * 8, 16);
+  cudaError_t e = buf.reserve(tb + align_up(n_events, 16) + 16);
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return MJP_ERR_NOMEM; }
+  char *base = (char *)buf.ptr;
+  cudaMemcpyAsync(base, times, (size_t)n_events * 8, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(base + tb, kinds, n_events, cudaMemcpyHostToDevice, h->stream);
+  double *d_out = (double *)(base + tb + align_up(n_events, 16));
+  mjp::mjp_end_time_probe<<<1, 32, 0, h->stream>>>((const uint8_t *)(base + tb), (const double *)base, n_events, clock,
+                                                   dur, d_out);
+  cudaMemcpyAsync(out, d_out, 8, cudaMemcpyDeviceToHost, h->stream);
+  e = cudaStreamSynchronize(h->stream);
+  buf.release();
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return MJP_ERR_CUDA; }
+  return MJP_OK;
+}
+
+}  // extern "C"

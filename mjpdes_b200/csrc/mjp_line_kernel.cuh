@@ -1,0 +1,546 @@
+// mjp_line_kernel.cuh -- the MJPdes run loop, one line instance per thread.
+//
+// Replaces core/main-loop-loop (core.clj:729-744) and everything it calls:
+// runables and its nine guards (core.clj:343-531), the actions (core.clj:215-326),
+// end-time / machine-future (core.clj:138-151,194-198), the up/down process
+// (core.clj:156-192), new-job (core.clj:328-340), log / push-log / clean-log-buf /
+// add-compute-log! (util/log.clj:30-109,159-217).  Paths are relative to the
+// reference's src/gov/nist/MJPdes/.
+//
+// How the reference's data structures map onto the machine:
+//  * the nine guard scans are boolean algebra on per-instance bitmasks
+//    (occupied / up / blocked / starved / buffer-full / feed-empty), bit i = machine i;
+//  * per-machine numbers (:future time+index, :status :ends, interval starts)
+//    live in shared memory as [slot][thread], so lanes that are looking at
+//    different machines never bank-conflict;
+//  * jobs are FIFO through a serial line, so a job is its id: the job on machine i
+//    is #started[i], buffer contents are consecutive ids, and :type / :enters sit in
+//    rings indexed by id;
+//  * end-time's look-ahead over future up/down events is resolved lazily: a job
+//    that does not fit in the current up-interval keeps its remaining work and is
+//    resolved when the machine's next :up event fires -- the same f64 operations in
+//    the same order as core.clj:145-151, so :ends is bit-identical, and every
+//    up/down event is generated exactly once;
+//  * a clock tick's messages are not stored: what clean-log-buf + add-compute-log!
+//    would do with them is a function of (machines seen, in which order; toggle
+//    counts of :bl/:ub and :st/:us per machine; which buffers got a :bj / :sm),
+//    all kept as bitmasks and applied when the next tick's first message arrives;
+//  * accumulators are added straight into the caller-visible output planes with
+//    fire-and-forget RED.ADD.F64 (one writer per address: order and rounding are
+//    those of the sequential sum).
+#pragma once
+#include "mjp_device.cuh"
+#include "mjp_params.h"
+#include "../../include/mjpdes_b200.h"
+
+namespace mjp {
+
+template <typename MaskT> struct MaskOps;
+template <> struct MaskOps<uint32_t> {
+  static __device__ __forceinline__ int ffs(uint32_t m) { return __ffs((int)m) - 1; }
+  static __device__ __forceinline__ int popc(uint32_t m) { return __popc(m); }
+};
+template <> struct MaskOps<uint64_t> {
+  static __device__ __forceinline__ int ffs(uint64_t m) { return __ffsll((long long)m) - 1; }
+  static __device__ __forceinline__ int popc(uint64_t m) { return __popcll(m); }
+};
+
+__device__ __forceinline__ void hmix(uint64_t &h, uint64_t w) { h = (h ^ w) * 0x100000001b3ull; }
+
+// fire-and-forget add into an output plane
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+// end-time (core.clj:138-151) split at the points where it needs an event that may not exist yet.
+// begin: at job start.  `machine_up`: :future is a :down event at fut_t.  Returns true when the job
+// does not fit before the next :down; v is then the work still to do, else v is :ends.
+__device__ __forceinline__ bool end_time_begin(bool machine_up, double fut_t, double clock, double na, double &v) {
+  if (machine_up) {
+    const double avail = fut_t - clock;                     // (- etime now)
+    if (avail > na) { v = clock + na; return false; }       // core.clj:147-148
+    v = na - avail; return true;                            // core.clj:149-150
+  }
+  v = na; return true;                                      // :up event first: now <- etime, core.clj:145-146
+}
+// resume: the machine's next :up event (t_up) and the :down after it (t_down) are known.
+__device__ __forceinline__ bool end_time_resume(double t_up, double t_down, double rem, double &v) {
+  const double avail = t_down - t_up;
+  if (avail > rem) { v = t_up + rem; return false; }
+  v = rem - avail; return true;
+}
+
+#define MJP_BIT(i) ((MaskT)1 << (i))
+
+template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP>
+__global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
+  using MO = MaskOps<MaskT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x, M = p.M, K = p.K;
+
+  // ---- CTA constant table --------------------------------------------------
+  double *c_lam = reinterpret_cast<double *>(smem_raw);
+  double *c_mu = c_lam + M;
+  double *c_dur = c_mu + M;          // [K*M]  w/W  (job-requires, utils.clj:95-101)
+  double *c_thr = c_dur + K * M;     // [K]    new-job thresholds (core.clj:332-339)
+  int *c_N = reinterpret_cast<int *>(c_thr + K);
+  int *c_lvl = c_N + M;
+  for (int q = tid; q < M; q += nt) { c_lam[q] = p.lam[q]; c_mu[q] = p.mu[q]; }
+  for (int q = tid; q < K * M; q += nt) c_dur[q] = p.dur[q];
+  for (int q = tid; q < K; q += nt) c_thr[q] = p.thr[q];
+  for (int q = tid; q < M - 1; q += nt) { c_N[q] = p.N[q]; c_lvl[q] = p.lvl[q]; }
+  __syncthreads();
+
+  const uint64_t g = (uint64_t)blockIdx.x * nt + tid;
+  if (g >= p.n_inst) return;
+  const uint64_t n_inst = p.n_inst;
+
+  // ---- per-thread state in shared memory: [slot][thread] -------------------
+  double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
+  uint32_t *su = reinterpret_cast<uint32_t *>(smem_raw + p.const_bytes + (size_t)p.nf64 * nt * 8) + tid;
+#define FUT_T(i)   sf[(i) * nt]                 /* :future etime                      */
+#define ENDS(i)    sf[(M + (i)) * nt]           /* :status :ends, or remaining work   */
+#define BS(i)      sf[(2 * M + (i)) * nt]       /* :bs (NaN = nil), util/log.clj:176  */
+#define SS(i)      sf[(3 * M + (i)) * nt]       /* :ss                                */
+#define LASTCLK(b) sf[(4 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
+#define FUT_N(i)   su[(i) * nt]                 /* :future index                      */
+#define STARTED(i) su[(M + (i)) * nt]           /* jobs started on machine i          */
+  uint32_t *s_cnt = su + (size_t)2 * M * nt;                      /* (count :holding), 4 per word */
+  const int cntw = (M - 1 + 3) >> 2;
+  uint32_t *s_jt = s_cnt + (size_t)cntw * nt;                     /* job type ring, 4 per word    */
+  uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * nt;              /* REPLAY: exponential cursor   */
+  const uint32_t Rm = (uint32_t)p.R - 1;
+
+  auto getb = [&](uint32_t *base, int idx) -> uint32_t {
+    return (base[(idx >> 2) * nt] >> ((idx & 3) * 8)) & 0xFFu;
+  };
+  auto setb = [&](uint32_t *base, int idx, uint32_t v) {
+    const int sh = (idx & 3) * 8;
+    uint32_t wd = base[(idx >> 2) * nt];
+    base[(idx >> 2) * nt] = (wd & ~(0xFFu << sh)) | (v << sh);
+  };
+  // line parameters, with the optional per-instance planes
+  auto lam_of = [&](int i) -> double { return (SWEEP && p.lam_i) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
+  auto mu_of = [&](int i) -> double { return (SWEEP && p.mu_i) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
+  auto cap_of = [&](int b) -> int { return (SWEEP && p.N_i) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
+  auto dur_of = [&](int k, int i) -> double {
+    if (SWEEP && (p.W_i || p.w_i)) {
+      const double wv = p.w_i ? p.w_i[(size_t)(k * M + i) * n_inst + g] : p.w[k * M + i];
+      const double Wv = p.W_i ? p.W_i[(size_t)i * n_inst + g] : p.W[i];
+      return __ddiv_rn(wv, Wv);
+    }
+    return c_dur[k * M + i];
+  };
+
+  const uint64_t gid = p.first_id + g;
+  const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
+  const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+  const MaskT ALL = (M >= (int)(8 * sizeof(MaskT))) ? ~(MaskT)0 : (MJP_BIT(M) - 1);
+  const MaskT bbs = (MaskT)p.bbs_mask;
+  const double INF = __longlong_as_double(0x7FF0000000000000ll);
+  const double QNAN = __longlong_as_double(0x7FF8000000000000ll);
+
+  // sojourn after the event (kind_was_up ? :up : :down) numbered n_prev at time t_prev  (core.clj:180-191)
+  auto next_event_time = [&](int i, uint32_t n_prev, bool prev_is_up, double t_prev) -> double {
+    const double rate = prev_is_up ? lam_of(i) : mu_of(i);
+    uint32_t o[4];
+    double T;
+    if (REPLAY) {
+      philox4x32_10(n_prev + 1, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
+      const double some_num = u53(o[0], o[1]);                                   // core.clj:185
+      uint32_t e = s_eidx[i * nt];
+      philox4x32_10(e++, 2u + 2u * i, g_lo, g_hi, k0, k1, o);
+      T = __ddiv_rn(-det_log(u52open(o[0], o[1])), rate);                        // core.clj:187
+      while (!(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {      // core.clj:188, 162-165
+        philox4x32_10(e++, 2u + 2u * i, g_lo, g_hi, k0, k1, o);
+        T = __dadd_rn(T, __ddiv_rn(-det_log(u52open(o[0], o[1])), rate));        // core.clj:190-191
+      }
+      s_eidx[i * nt] = e;
+    } else {
+      philox4x32_10(n_prev + 1, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
+      T = __ddiv_rn(-det_log(__dmul_rn(u52open(o[0], o[1]), u52open(o[2], o[3]))), rate);   // Erlang-2
+    }
+    return __dadd_rn(t_prev, T);
+  };
+
+  // ---- preprocess-model: first up/down event of each machine (core.clj:156-160,557-562) ----
+  MaskT up = 0;
+  for (int i = 0; i < M; ++i) {
+    const double lam = lam_of(i), mu = mu_of(i);
+    const double p_up = __ddiv_rn(mu, __dadd_rn(lam, mu));
+    uint32_t o[4];
+    philox4x32_10(0u, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
+    const bool is_up = u53(o[0], o[1]) < p_up;
+    double eu;
+    if (REPLAY) {
+      uint32_t o2[4];
+      philox4x32_10(0u, 2u + 2u * i, g_lo, g_hi, k0, k1, o2);
+      eu = u52open(o2[0], o2[1]);
+      s_eidx[i * nt] = 1u;
+    } else {
+      eu = u52open(o[2], o[3]);
+    }
+    FUT_T(i) = __ddiv_rn(-det_log(eu), is_up ? lam : mu);
+    FUT_N(i) = 0u;
+    STARTED(i) = 0u;
+    ENDS(i) = 0.0;
+    BS(i) = QNAN;
+    SS(i) = QNAN;
+    if (is_up) up |= MJP_BIT(i);
+  }
+  for (int b = 0; b < M - 1; ++b) LASTCLK(b) = p.warm_up;
+  for (int q = 0; q < cntw; ++q) s_cnt[q * nt] = 0u;
+
+  // ---- model state in registers ---------------------------------------------
+  double clock = 0.0;
+  MaskT occ = 0, B = 0, S = 0, full = 0, pend = 0, dup = 0, fired = 0;
+  MaskT empty = ALL & ~(MaskT)1;               // feed-buffer-empty? (nil for the entry machine, utils.clj:85)
+  const MaskT upj = p.jm2dm ? ALL : (MaskT)0;  // :jm2dm, core.clj:490,495
+  uint32_t curjob = 0;
+  uint64_t n_events = 0, iters = 0;
+  uint64_t h = 0xcbf29ce484222325ull;
+  // tick state (what :log-buf holds, util/log.clj:89-109)
+  double tick_clk = 0.0, ej_ent = 0.0;
+  MaskT seen = 0, lead = 0, has_bj = 0, has_sm = 0, rtbj = 0;
+  MaskT tgB_lo = 0, tgB_hi = 0, tgS_lo = 0, tgS_hi = 0, B0 = 0, S0 = 0;
+  bool has_ej = false;
+  // steady accumulators kept in registers
+  double residence = 0.0;
+  long long njobs = 0;
+  int status = MJP_INST_NOT_RUN;
+
+  auto mark_seen = [&](int i) {       // (group-by :m) order, util/log.clj:44
+    const MaskT bit = MJP_BIT(i);
+    if (!(seen & bit)) {
+      if (((seen >> 1) >> i) & 1) lead &= ~bit; else lead |= bit;
+      seen |= bit;
+    }
+  };
+  auto toggle = [&](MaskT &lo, MaskT &hi, MaskT bit) {   // saturating 2-bit counter per machine
+    const MaskT carry = lo & bit, sat = hi & lo & bit;
+    lo = (lo ^ bit) | sat;
+    hi |= carry;
+  };
+  // push-log for the tick that just ended (util/log.clj:98-108): clean-log-buf + add-compute-log!
+  auto flush_tick = [&]() {
+    if (tick_clk >= p.warm_up) {                                           // util/log.clj:104
+      // :bl/:ub of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed in order
+      MaskT q = tgB_lo;
+      while (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const double bs = BS(i);
+        if (((B0 >> i) & 1) && bs == bs) red_add(p.blocked + (size_t)i * n_inst + g, tick_clk - bs);   // block-
+        BS(i) = ((B >> i) & 1) ? tick_clk : QNAN;                                                       // block+
+      }
+      q = tgS_lo;
+      while (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const double ss = SS(i);
+        if (((S0 >> i) & 1) && ss == ss) red_add(p.starved + (size_t)i * n_inst + g, tick_clk - ss);   // starve-
+        SS(i) = ((S >> i) & 1) ? tick_clk : QNAN;                                                       // starve+
+      }
+      // buf+ / buf- (util/log.clj:159-171): the first message on a buffer in cleaned order gets the
+      // elapsed time, the others add (clk - clk) = 0.
+      q = has_bj | has_sm;
+      while (q) {
+        const int b = MO::ffs(q); q &= q - 1;
+        const int cf = (int)getb(s_cnt, b);
+        const bool bj = (has_bj >> b) & 1, sm = (has_sm >> b) & 1;
+        int n;
+        if (bj && !sm) n = cf - 1;
+        else if (sm && !bj) n = cf + 1;
+        else {
+          const bool bj_first_rt = (rtbj >> b) & 1;
+          const int n_bj = bj_first_rt ? cf : cf - 1, n_sm = bj_first_rt ? cf + 1 : cf;
+          n = ((lead >> b) & 1) ? n_bj : n_sm;        // machine b logged before machine b+1 in this tick?
+        }
+        const double lc = LASTCLK(b);
+        red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
+        LASTCLK(b) = tick_clk;
+      }
+      if (has_ej) { residence = residence + (tick_clk - ej_ent); njobs++; }   // end-job util/log.clj:212-217
+    }
+    seen = lead = has_bj = has_sm = rtbj = 0;
+    tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
+    has_ej = false;
+    B0 = B; S0 = S;
+  };
+  // end-time at job start (core.clj:138-151), lazily: fits in the current up interval, or pending
+  auto start_job = [&](int i, int type) {
+    const MaskT bit = MJP_BIT(i);
+    double v;
+    if (end_time_begin((up & bit) != 0, FUT_T(i), clock, dur_of(type, i), v)) pend |= bit; else pend &= ~bit;
+    ENDS(i) = v;
+  };
+
+  // ======================= main-loop-loop, core.clj:729-744 =======================
+  for (;;) {
+    // end-main-loop? core.clj:722-727
+    if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
+      status = MJP_INST_NORMAL_END; break;
+    }
+    if (++iters > p.max_iter) { status = MJP_INST_ITER_LIMIT; break; }
+
+    // ---- runables (core.clj:515-531): guards on the pre-batch state ----
+    const MaskT notfull = ~full, nonempty = ~empty;
+    const MaskT c_aj = (~occ & ~B & up & (~bbs | notfull)) & (MaskT)1;                       // core.clj:343-354
+    const MaskT c_tm = (up | upj) & ~(MaskT)1 & ~B & ~S & ~occ & nonempty & (~bbs | notfull) & ALL;   // core.clj:485-506
+    MaskT fin = ~occ;                                                                         // utils.clj:68-74
+    {
+      MaskT q = ~S & empty & occ & ~pend;
+      while (q) { const int i = MO::ffs(q); q &= q - 1; if (clock >= ENDS(i)) fin |= MJP_BIT(i); }
+    }
+    const MaskT c_st = ~S & empty & fin & ALL;                                                // core.clj:451-460
+    const MaskT c_us = S & nonempty;                                                          // core.clj:462-470
+    const MaskT c_ub = B & notfull & ALL;                                                     // core.clj:426-449
+    const MaskT c_blb = bbs & ~B & ~occ & nonempty & full;     // BBS, time = clock          core.clj:387-394,406-411
+    const MaskT c_bla = ~bbs & ~B & full & occ & ~pend & ALL;  // BAS, time = :ends          core.clj:376-383,401-405
+    const MaskT c_tb = occ & ~B & notfull & ~pend & ALL;       // time = max(clock, :ends)   core.clj:472-483
+    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup) != 0;
+
+    // min over the timed candidates, remembering who attains it
+    double tmin = INF;
+    MaskT m_ud = 0, m_tb = 0, m_bl = 0;
+    for (int i = 0; i < M; ++i) {                                                             // core.clj:356-372
+      const double t = FUT_T(i);
+      if (t < tmin) { tmin = t; m_ud = 0; }
+      if (t == tmin) m_ud |= MJP_BIT(i);
+    }
+    m_ud &= ~dup;
+    {
+      MaskT q = c_tb;
+      while (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const double t = fmax(clock, ENDS(i));
+        if (t < tmin) { tmin = t; m_ud = m_tb = 0; }
+        if (t == tmin) m_tb |= MJP_BIT(i);
+      }
+      q = c_bla;
+      while (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const double t = ENDS(i);
+        if (t < tmin) { tmin = t; m_ud = m_tb = m_bl = 0; }
+        if (t == tmin) m_bl |= MJP_BIT(i);
+      }
+    }
+    double tstar = tmin;
+    if (now_any) {
+      if (clock < tmin) { tstar = clock; m_ud = m_tb = m_bl = 0; }
+      else if (clock > tmin) { status = MJP_INST_CLOCK_BACK; break; }                         // core.clj:133
+    }
+    if (tstar == INF) { status = MJP_INST_NO_RUNABLES; break; }
+    if (clock > tstar) { status = MJP_INST_CLOCK_BACK; break; }
+    const bool at_now = now_any;       // candidates at time `clock` are in the batch iff clock == tstar
+    const MaskT b_aj = at_now ? c_aj : 0, b_tm = at_now ? c_tm : 0, b_st = at_now ? c_st : 0;
+    const MaskT b_us = at_now ? c_us : 0, b_ub = at_now ? c_ub : 0;
+    const MaskT b_bl = m_bl | (at_now ? c_blb : 0);
+    const MaskT b_ud = m_ud | (at_now ? dup : 0);
+    const MaskT b_up = b_ud & ~up, b_dn = b_ud & up;
+    const MaskT b_tb = m_tb;
+
+    // ---- advance-clock core.clj:128-135 ----
+    if (tstar != clock) fired = 0;
+    clock = tstar;
+    const bool will_log = p.up_down ? true : ((b_aj | b_tb | b_tm | b_st | b_us | b_bl | b_ub) != 0);
+    if (will_log) {
+      if (seen != 0 && clock != tick_clk) flush_tick();       // push-log of the previous tick
+      tick_clk = clock;
+    }
+    n_events += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
+                MO::popc(b_us) + MO::popc(b_bl) + MO::popc(b_ub);
+
+    // ---- run the batch in generator order, core.clj:742 ----
+    if (b_aj) {                                              // add-job core.clj:240-254, new-job core.clj:328-340
+      int type = -1;
+      if (K == 1 && c_thr[0] >= 1.0) type = 0;
+      else {
+        uint32_t o[4];
+        philox4x32_10(curjob, 0u, g_lo, g_hi, k0, k1, o);
+        const double choose = u53(o[0], o[1]);
+        for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) { type = k; break; }
+      }
+      if (type < 0) { status = MJP_INST_JOBTYPE_NIL; break; }
+      const uint32_t id = curjob + 1;
+      start_job(0, type);
+      if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
+      mark_seen(0);
+      curjob = id; occ |= 1; STARTED(0) = id;
+      setb(s_jt, (int)(id & Rm), (uint32_t)type);
+      p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
+      if (fired & 1) { dup |= 1; up ^= 1; }                  // machine-future core.clj:194-198
+    }
+    {                                                        // bring-machine-up / -down core.clj:215-238
+      MaskT q = b_up;
+      for (int pass = 0; pass < 2; ++pass) {
+        while (q) {
+          const int i = MO::ffs(q); q &= q - 1;
+          const MaskT bit = MJP_BIT(i);
+          const bool was_up_event = !(up & bit);
+          if (HASH) {
+            hmix(h, (uint64_t)(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN) | ((uint64_t)i << 8));
+            hmix(h, d2bits(clock)); hmix(h, 0);
+          }
+          if (p.up_down) mark_seen(i);
+          fired |= bit;
+          if (dup & bit) { dup &= ~bit; up ^= bit; continue; }       // re-fire of an already realised event
+          const double t_fire = FUT_T(i);
+          const uint32_t n = FUT_N(i);
+          const double t_next = next_event_time(i, n, was_up_event, t_fire);
+          FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
+          if (was_up_event && (pend & bit)) {                // end-time resumes at this :up  core.clj:145-151
+            double v;
+            if (!end_time_resume(t_fire, t_next, ENDS(i), v)) pend &= ~bit;
+            ENDS(i) = v;
+          }
+        }
+        q = b_dn;
+      }
+    }
+    {                                                        // advance2buffer core.clj:285-300
+      MaskT q = b_tb;
+      while (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const MaskT bit = MJP_BIT(i);
+        const uint32_t id = STARTED(i);
+        if (i < M - 1) {
+          const int n = (int)getb(s_cnt, i);
+          if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ENDS(i))); }
+          mark_seen(i);
+          if (has_bj & bit) status = MJP_INST_TICK_OVERFLOW;
+          has_bj |= bit;
+          if (!(has_sm & bit)) rtbj |= bit;
+          setb(s_cnt, i, (uint32_t)(n + 1));
+          if (n + 1 == cap_of(i)) full |= bit;
+          empty &= ~(bit << 1);
+        } else {
+          const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
+          if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(ENDS(i))); }
+          mark_seen(i);
+          if (has_ej) status = MJP_INST_TICK_OVERFLOW;
+          has_ej = true; ej_ent = ent;
+        }
+        occ &= ~bit;
+      }
+    }
+    {                                                        // advance2machine core.clj:263-277
+      MaskT q = b_tm;
+      while (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const MaskT bit = MJP_BIT(i), bbit = bit >> 1;
+        const int b = i - 1;
+        const int n = (int)getb(s_cnt, b);
+        const uint32_t id = STARTED(i) + 1;
+        const int type = (int)getb(s_jt, (int)(id & Rm));
+        start_job(i, type);
+        if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
+        mark_seen(i);
+        if (has_sm & bbit) status = MJP_INST_TICK_OVERFLOW;
+        has_sm |= bbit;
+        setb(s_cnt, b, (uint32_t)(n - 1));
+        if (n - 1 == 0) empty |= bit;
+        full &= ~bbit;
+        occ |= bit; STARTED(i) = id;
+        if (fired & bit) { dup |= bit; up ^= bit; }
+      }
+    }
+    {                                                        // record-actions core.clj:304-326
+      MaskT q = b_st;
+      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_ST | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); S |= MJP_BIT(i); toggle(tgS_lo, tgS_hi, MJP_BIT(i)); }
+      q = b_us;
+      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_US | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); S &= ~MJP_BIT(i); toggle(tgS_lo, tgS_hi, MJP_BIT(i)); }
+      q = b_bl;
+      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_BL | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); B |= MJP_BIT(i); toggle(tgB_lo, tgB_hi, MJP_BIT(i)); }
+      q = b_ub;
+      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_UB | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); B &= ~MJP_BIT(i); toggle(tgB_lo, tgB_hi, MJP_BIT(i)); }
+    }
+    if (status == MJP_INST_TICK_OVERFLOW) break;
+    if (seen == 0) { status = MJP_INST_LOGBUF_EMPTY; break; }   // push-log returned nil, util/log.clj:95
+  }
+
+  // the reference never flushes the last tick: whatever is still in :log-buf is lost
+  if (p.njobs) p.njobs[g] = njobs;
+  if (p.residence) p.residence[g] = residence;
+  if (p.final_clock) p.final_clock[g] = clock;
+  if (p.curjob) p.curjob[g] = (long long)curjob;
+  if (p.n_events) p.n_events[g] = n_events;
+  if (HASH && p.hash) p.hash[g] = h;
+  p.status[g] = (uint8_t)status;
+#undef FUT_T
+#undef ENDS
+#undef BS
+#undef SS
+#undef LASTCLK
+#undef FUT_N
+#undef STARTED
+}
+
+// ---- aggregate: calc-basics (core.clj:617-634) per instance, then sum(x), sum(x^2) -------------
+// One block-wide tree per metric; partials[block][metric] are summed in a fixed
+// order by mjp_aggregate_final, so the result does not depend on scheduling.
+__global__ void mjp_aggregate_partial(const KParams p, double *partials, int n_metrics) {
+  extern __shared__ double red[];      // [2][blockDim]
+  const int tid = threadIdx.x, nt = blockDim.x, M = p.M;
+  const uint64_t n = p.n_inst;
+  const double run_time = p.run_to - p.warm_up;
+  for (int metric = -1; metric < n_metrics; ++metric) {
+    double s1 = 0.0, s2 = 0.0;
+    for (uint64_t g = (uint64_t)blockIdx.x * nt + tid; g < n; g += (uint64_t)gridDim.x * nt) {
+      if (p.status[g] != MJP_INST_NORMAL_END) continue;
+      double x;
+      if (metric < 0) x = 1.0;
+      else if (metric == 0) x = (double)p.njobs[g] / run_time;
+      else if (metric == 1) x = p.njobs[g] ? p.residence[g] / (double)p.njobs[g] : 0.0;
+      else if (metric < 2 + M) x = p.blocked[(size_t)(metric - 2) * n + g] / run_time;
+      else if (metric < 2 + 2 * M) x = p.starved[(size_t)(metric - 2 - M) * n + g] / run_time;
+      else {
+        const int b = metric - 2 - 2 * M;
+        const int lv = p.lvl[b], cap = p.N[b];
+        double acc = 0.0;
+        for (int k = 0; k <= cap; ++k) acc = acc + (double)k * p.occ[(size_t)(lv + k) * n + g];
+        x = acc / run_time;
+      }
+      s1 += x; s2 += x * x;
+    }
+    red[tid] = s1; red[nt + tid] = s2;
+    __syncthreads();
+    for (int off = nt >> 1; off > 0; off >>= 1) {
+      if (tid < off) { red[tid] += red[tid + off]; red[nt + tid] += red[nt + tid + off]; }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int slot = (metric < 0) ? 0 : 1 + 2 * metric;
+      double *row = partials + (size_t)blockIdx.x * (1 + 2 * n_metrics);
+      row[slot] = red[0];
+      if (metric >= 0) row[slot + 1] = red[nt];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void mjp_aggregate_final(const double *partials, int n_blocks, int len, double *out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= len) return;
+  double s = 0.0;
+  for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * len + q];
+  out[q] = s;
+}
+
+// ---- probe: end-time (core.clj:138-151) over a literal :up&down schedule ------------------------
+__global__ void mjp_end_time_probe(const uint8_t *kinds, const double *times, int n, double clock, double dur,
+                                   double *out) {
+  if (blockIdx.x || threadIdx.x) return;
+  const double QNAN = __longlong_as_double(0x7FF8000000000000ll);
+  int k = 0;
+  while (k < n && times[k] < clock) ++k;                     // drop-while core.clj:143
+  if (k >= n) { *out = QNAN; return; }
+  double v;
+  bool pending;
+  if (kinds[k] == 1) { pending = end_time_begin(true, times[k], clock, dur, v); ++k; }   // :future is :down
+  else pending = end_time_begin(false, 0.0, clock, dur, v);
+  while (pending) {                                          // k is at the next :up event
+    if (k + 1 >= n) { v = QNAN; break; }
+    pending = end_time_resume(times[k], times[k + 1], v, v);
+    k += 2;
+  }
+  *out = v;
+}
+
+}  // namespace mjp

@@ -1,0 +1,43 @@
+// mjp_params.h -- kernel parameter block shared by host and device code.
+#pragma once
+#include <cstdint>
+
+namespace mjp {
+
+struct KParams {
+  // batch
+  uint64_t n_inst;        // instances in this launch
+  uint64_t first_id;      // RNG instance id of instance 0
+  uint64_t seed;
+  uint64_t max_iter;      // watchdog on loop iterations per instance
+  // line (flat form of the preprocessed Model, core.clj:578-615)
+  int32_t M, K;
+  int32_t R;              // job ring size: power of two >= M + sum N (jobs in the line)
+  int32_t L;              // occupancy levels, sum (N[b]+1)
+  double warm_up, run_to;
+  int64_t run_to_job;     // -1 unset
+  uint64_t bbs_mask;      // bit i: machine i is :BBS
+  int32_t jm2dm, up_down, log_on, reserved;
+  uint64_t max_lines;
+  // shared constants (device pointers)
+  const double *lam, *mu, *W, *w, *dur, *thr;   // [M] [M] [M] [K*M] [K*M]=w/W [K]=new-job thresholds
+  const int32_t *N, *lvl;                       // [M-1] capacity, [M-1] first level row of buffer b
+  // per-instance override planes, instance-fastest (nullptr = absent)
+  const double *lam_i, *mu_i, *W_i, *w_i;
+  const int32_t *N_i;
+  // outputs, instance-fastest (zero-initialised by the host before launch)
+  int64_t *njobs; double *residence; double *blocked, *starved, *occ; double *final_clock;
+  int64_t *curjob; uint64_t *n_events; uint64_t *hash; uint8_t *status;
+  // scratch
+  double *enters;         // [R][n_inst] :enters of the jobs in the line
+  // SCADA records
+  void *log_records;      // mjp_log_record[log_capacity]
+  uint64_t log_capacity;
+  unsigned long long *log_cursor;   // [0] next free record, [1] records dropped
+  // shared-memory layout
+  int32_t nf64, nu32;     // per-thread slots
+  int32_t const_bytes;    // CTA constant table size (multiple of 16)
+  int32_t stage_cap;      // LOG mode: messages staged per tick per instance
+};
+
+}  // namespace mjp

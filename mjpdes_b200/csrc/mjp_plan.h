@@ -1,0 +1,73 @@
+// mjp_plan.h -- host-side compilation of a line descriptor into the kernel's
+// constant table and shared-memory layout ("preprocess-model" for the device,
+// core.clj:578-615).  Pure host C++, no CUDA calls.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/mjpdes_b200.h"
+#include "mjp_params.h"
+
+namespace mjp {
+
+struct LinePlan {
+  KParams kp{};                 // everything except device pointers, seed and first_id
+  std::vector<double> cd;       // lam[M] mu[M] W[M] w[K*M] dur[K*M] thr[K]
+  std::vector<int32_t> ci;      // N[M-1] lvl[M-1]
+  size_t per_thread_bytes = 0;
+
+  // offsets (in doubles) of the sections of cd
+  size_t off_lam() const { return 0; }
+  size_t off_mu() const { return (size_t)kp.M; }
+  size_t off_W() const { return 2 * (size_t)kp.M; }
+  size_t off_w() const { return 3 * (size_t)kp.M; }
+  size_t off_dur() const { return off_w() + (size_t)kp.K * kp.M; }
+  size_t off_thr() const { return off_dur() + (size_t)kp.K * kp.M; }
+};
+
+inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
+  LinePlan pl;
+  KParams &kp = pl.kp;
+  const int M = L->M, K = L->K;
+  kp.n_inst = n_inst;
+  kp.M = M; kp.K = K;
+  kp.warm_up = L->warm_up; kp.run_to = L->run_to; kp.run_to_job = L->run_to_job;
+  kp.jm2dm = L->jm2dm ? 1 : 0; kp.up_down = L->up_down ? 1 : 0; kp.log_on = L->log ? 1 : 0;
+  kp.max_lines = L->max_lines;
+  for (int i = 0; i < M; ++i) if (L->discipline[i] == MJP_BBS) kp.bbs_mask |= (1ull << i);
+  int sumN = 0, levels = 0;
+  pl.ci.assign(L->N, L->N + (M - 1));
+  for (int b = 0; b < M - 1; ++b) { pl.ci.push_back(levels); levels += L->N[b] + 1; sumN += L->N[b]; }
+  kp.L = levels;
+  int R = 4;
+  while (R < M + sumN) R <<= 1;        // jobs in the line <= M + sum N
+  kp.R = R;
+  {
+    // watchdog: the loop makes ~1.3 iterations per machine per time unit; allow far more
+    double rate = 0.0;
+    for (int i = 0; i < M; ++i) rate += 4.0 + L->lambda[i] + L->mu[i];
+    double it = 512.0 * (L->run_to + 1.0) * rate + 1e6;
+    if (L->run_to_job >= 0) it += 64.0 * (double)L->run_to_job * M;
+    kp.max_iter = it > 9e18 ? (uint64_t)9e18 : (uint64_t)it;
+  }
+  pl.cd.insert(pl.cd.end(), L->lambda, L->lambda + M);
+  pl.cd.insert(pl.cd.end(), L->mu, L->mu + M);
+  pl.cd.insert(pl.cd.end(), L->W, L->W + M);
+  pl.cd.insert(pl.cd.end(), L->w, L->w + (size_t)K * M);
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < M; ++i) pl.cd.push_back(L->w[k * M + i] / L->W[i]);      // job-requires utils.clj:95-101
+  {
+    // new-job thresholds, core.clj:332-339: accum starts at p0, then adds the CURRENT portion
+    double accum = L->portion[0];
+    for (int k = 0; k < K; ++k) { pl.cd.push_back(accum); accum = accum + L->portion[k]; }
+  }
+  kp.nf64 = 5 * M - 1;
+  kp.nu32 = 2 * M + ((M - 1 + 3) >> 2) + (R >> 2) + M;     // last M: REPLAY exponential cursors
+  kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
+  pl.per_thread_bytes = (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
+  return pl;
+}
+
+}  // namespace mjp

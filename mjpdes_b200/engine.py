@@ -1,0 +1,137 @@
+"""Thin object wrapper over the C ABI (``include/mjpdes_b200.h``).
+
+``Handle.run`` is the call that replaces ``core/main-loop-loop`` (core.clj:729-744)
+for a batch of independent line instances.  Everything here goes through
+``libmjpdes_b200.so``; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class RunResult:
+    """Per-instance ``*log-steady*`` content plus loop status, as numpy arrays."""
+
+    def __init__(self, line: abi.HostLine, stats: abi.HostStats, log: np.ndarray | None, rc: int,
+                 kernel_ms: float, launches: int):
+        self.line, self.stats, self.log, self.rc = line, stats, log, rc
+        self.kernel_ms, self.launches = kernel_ms, launches
+
+    @property
+    def n_inst(self) -> int:
+        return self.stats.n_inst
+
+    @property
+    def total_events(self) -> int:
+        return int(self.stats.n_events.sum())
+
+
+class Handle:
+    """One CUDA device, one stream.  Not thread-safe; distinct handles are."""
+
+    def __init__(self, device: int = 0, event_hash: bool = False, lib_path: str | None = None):
+        self._lib = abi.load_library(lib_path)
+        if self._lib.mjp_device_count() <= device:
+            raise abi.MjpError(abi.ERR_CUDA, f"CUDA device {device} not present "
+                               f"({self._lib.mjp_device_count()} visible); mjpdes_b200 has no CPU path")
+        cfg = abi.Config(device, abi.CFG_EVENT_HASH if event_hash else 0, 0)
+        self._h = C.c_void_p()
+        rc = self._lib.mjp_create(C.byref(cfg), C.byref(self._h))
+        if rc != abi.OK:
+            raise abi.MjpError(rc, (self._lib.mjp_last_error(None) or b"").decode())
+        self.device = device
+        self.event_hash = event_hash
+        self._line = None
+        self._n = 0
+
+    # -- lifecycle ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mjp_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow=(abi.OK,)):
+        if rc not in allow:
+            raise abi.MjpError(rc, (self._lib.mjp_last_error(self._h) or b"").decode())
+        return rc
+
+    # -- the drop-in call ----------------------------------------------------------
+    def run(self, line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int = 0,
+            first_instance_id: int = 0, log_capacity: int = 0, want_aggregate: bool = True) -> RunResult:
+        """Blocking: host buffers in, host buffers out (copies included)."""
+        n = int(n_inst)
+        stats = abi.HostStats(line, n, want_hash=True, want_aggregate=want_aggregate)
+        rng = abi.RngSpec(mode, 0, seed, first_instance_id)
+        desc, st = line.desc(), stats.struct()
+        hlog = abi.HostLog(log_capacity) if log_capacity else None
+        rc = self._check(self._lib.mjp_run(self._h, C.byref(desc), n, C.byref(rng), C.byref(st),
+                                           C.byref(hlog.struct()) if hlog else None),
+                         allow=(abi.OK, abi.LOG_TRUNCATED))
+        self._line, self._n = line, n
+        return RunResult(line, stats, hlog.view().copy() if hlog else None, rc, self.kernel_ms(), self.launch_count())
+
+    # -- device-resident variant (measurement) --------------------------------------
+    def upload(self, line: abi.HostLine, n_inst: int):
+        desc = line.desc()
+        self._check(self._lib.mjp_upload(self._h, C.byref(desc), int(n_inst)))
+        self._line, self._n = line, int(n_inst)
+
+    def launch(self, mode: int = abi.RNG_COUNTER, seed: int = 0, first_instance_id: int = 0, want_log: bool = False):
+        rng = abi.RngSpec(mode, 0, seed, first_instance_id)
+        self._check(self._lib.mjp_launch(self._h, C.byref(rng), int(want_log)))
+
+    def sync(self):
+        self._check(self._lib.mjp_sync(self._h))
+
+    def download(self, stats: abi.HostStats | None = None, log_capacity: int = 0) -> RunResult:
+        stats = stats or abi.HostStats(self._line, self._n)
+        st = stats.struct()
+        hlog = abi.HostLog(log_capacity) if log_capacity else None
+        rc = self._check(self._lib.mjp_download(self._h, C.byref(st), C.byref(hlog.struct()) if hlog else None),
+                         allow=(abi.OK, abi.LOG_TRUNCATED))
+        return RunResult(self._line, stats, hlog.view().copy() if hlog else None, rc, self.kernel_ms(),
+                         self.launch_count())
+
+    def download_fields(self, names) -> abi.HostStats:
+        """Copy back only the named planes of the last launch (e.g. ("n_events", "aggregate"))."""
+        stats = abi.HostStats(self._line, self._n)
+        st = stats.struct()
+        for f, _ in abi.StatsOut._fields_:
+            if f not in names:
+                setattr(st, f, None)
+        self._check(self._lib.mjp_download(self._h, C.byref(st), None))
+        return stats
+
+    def kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        self._check(self._lib.mjp_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        n = C.c_int(0)
+        self._check(self._lib.mjp_last_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def probe_end_time(self, kinds, times, clock: float, dur: float) -> float:
+        k = np.ascontiguousarray(kinds, np.uint8)
+        t = np.ascontiguousarray(times, np.float64)
+        out = C.c_double(0)
+        self._check(self._lib.mjp_probe_end_time(self._h, abi.ptr(k, C.c_uint8), abi.ptr(t, C.c_double), len(k),
+                                                 clock, dur, C.byref(out)))
+        return float(out.value)

@@ -271,13 +271,17 @@ struct Sim {
   double job_requires(const Job &j, int i) const { return w[(size_t)j.type * M + i] / mach[i].W; } /* utils:95-101 */
 
   /* ---- event hash: every run-action call, in execution order ---- */
-  void count_event(int act, int m, int64_t j, int n, double clk, double aux) {
+  /* FNV-1a style over 64-bit words: {act|m<<8|n<<16|j<<32, bits(clk), bits(aux)}; aux is the
+   * completed job's :ends for :bj, :ent for :ej (which also mixes :ends), 0 otherwise, so every
+   * end-time result is checked at the moment the job leaves its machine. */
+  void count_event(int act, int m, int64_t j, int n, double clk, double aux, double aux2 = 0.0) {
     n_events++; act_counts[act]++;
     uint64_t w0 = (uint64_t)act | ((uint64_t)(uint8_t)m << 8) | ((uint64_t)(uint16_t)n << 16) |
                   ((uint64_t)(uint32_t)j << 32);
     hash = (hash ^ w0) * 0x100000001b3ull;
     hash = (hash ^ d2b(clk)) * 0x100000001b3ull;
-    hash = (hash ^ d2b(aux)) * 0x100000001b3ull;
+    hash = (hash ^ (act == MJP_ACT_BJ || act == MJP_ACT_EJ ? d2b(aux) : 0ull)) * 0x100000001b3ull;
+    if (act == MJP_ACT_EJ) hash = (hash ^ d2b(aux2)) * 0x100000001b3ull;
   }
 
   /* ---- log/log, log:30-36 ---- */
@@ -348,10 +352,10 @@ struct Sim {
   void advance2buffer(int i) {                           /* core:285-300 */
     Job j = mach[i].job;
     if (i < M - 1) {
-      count_event(MJP_ACT_BJ, i, j.id, (int)holding[i].size(), clock, 0.0);
+      count_event(MJP_ACT_BJ, i, j.id, (int)holding[i].size(), clock, j.ends);
       log({MJP_ACT_BJ, i, j.id, (int)holding[i].size(), kNaN, clock});
     } else {
-      count_event(MJP_ACT_EJ, i, j.id, 0, clock, j.enters);
+      count_event(MJP_ACT_EJ, i, j.id, 0, clock, j.enters, j.ends);
       log({MJP_ACT_EJ, i, j.id, 0, j.enters, clock});
     }
     mach[i].occ = false;

@@ -1,0 +1,58 @@
+// hostsim.cpp -- TEST-ONLY host execution of the kernel source (see cuda_shim.h).
+#include "cuda_shim.h"
+#include "../../mjpdes_b200/csrc/mjp_line_kernel.cuh"
+#include "../../mjpdes_b200/csrc/mjp_plan.h"
+
+#include <vector>
+
+extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
+                           int want_hash) {
+  mjp::LinePlan pl = mjp::build_plan(L, n_inst);
+  mjp::KParams kp = pl.kp;
+  const int M = kp.M;
+  kp.seed = rng->seed; kp.first_id = rng->first_instance_id;
+  const double *dc = pl.cd.data();
+  kp.lam = dc + pl.off_lam(); kp.mu = dc + pl.off_mu(); kp.W = dc + pl.off_W(); kp.w = dc + pl.off_w();
+  kp.dur = dc + pl.off_dur(); kp.thr = dc + pl.off_thr();
+  kp.N = pl.ci.data(); kp.lvl = pl.ci.data() + (M - 1);
+  kp.lam_i = L->lambda_inst; kp.mu_i = L->mu_inst; kp.W_i = L->W_inst; kp.w_i = L->w_inst; kp.N_i = L->N_inst;
+  const bool sweep = kp.lam_i || kp.mu_i || kp.W_i || kp.w_i || kp.N_i;
+  std::vector<double> enters((size_t)kp.R * n_inst);
+  kp.enters = enters.data();
+  for (size_t q = 0; q < (size_t)M * n_inst; ++q) { s->blocked_time[q] = 0; s->starved_time[q] = 0; }
+  for (size_t q = 0; q < (size_t)kp.L * n_inst; ++q) s->occ_time[q] = 0;
+  kp.njobs = s->njobs; kp.residence = s->residence_sum; kp.blocked = s->blocked_time; kp.starved = s->starved_time;
+  kp.occ = s->occ_time; kp.final_clock = s->final_clock; kp.curjob = s->current_job; kp.n_events = s->n_events;
+  kp.hash = s->event_hash; kp.status = s->status;
+  if (pl.kp.const_bytes + pl.per_thread_bytes > sizeof(mjp::smem_raw)) return MJP_ERR_UNSUPPORTED;
+  const bool replay = rng->mode == MJP_RNG_REPLAY, hash = want_hash != 0;
+  gridDim.x = (unsigned)n_inst;
+  for (uint64_t g = 0; g < n_inst; ++g) {
+    blockIdx.x = (unsigned)g;
+#define RUN(MT) \
+    if (replay && hash && sweep) mjp::mjp_line_kernel<MT, true, true, true>(kp); \
+    else if (replay && hash) mjp::mjp_line_kernel<MT, true, true, false>(kp); \
+    else if (replay && sweep) mjp::mjp_line_kernel<MT, true, false, true>(kp); \
+    else if (replay) mjp::mjp_line_kernel<MT, true, false, false>(kp); \
+    else if (hash && sweep) mjp::mjp_line_kernel<MT, false, true, true>(kp); \
+    else if (hash) mjp::mjp_line_kernel<MT, false, true, false>(kp); \
+    else if (sweep) mjp::mjp_line_kernel<MT, false, false, true>(kp); \
+    else mjp::mjp_line_kernel<MT, false, false, false>(kp);
+    if (M <= 32) { RUN(uint32_t) } else { RUN(uint64_t) }
+  }
+  if (s->aggregate) {
+    const int n_metrics = 3 * M + 1, len = 1 + 2 * n_metrics;
+    std::vector<double> partials(len);
+    blockIdx.x = 0; gridDim.x = 1;
+    mjp::mjp_aggregate_partial(kp, partials.data(), n_metrics);
+    for (int q = 0; q < len; ++q) s->aggregate[q] = partials[q];
+  }
+  return MJP_OK;
+}
+
+extern "C" double hostsim_end_time(const uint8_t *kinds, const double *times, int n, double clock, double dur) {
+  double out = 0;
+  blockIdx.x = 0;
+  mjp::mjp_end_time_probe(kinds, times, n, clock, dur, &out);
+  return out;
+}

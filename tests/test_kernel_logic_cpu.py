@@ -1,0 +1,81 @@
+"""CPU-side check of the KERNEL SOURCE: mjp_line_kernel.cuh compiled as host C++ through
+tests/hostsim/cuda_shim.h (one thread per block) must reproduce the oracle's event sequence
+(hash) and accumulators bit-for-bit.  This guards the kernel's control logic where no GPU
+exists; the GPU parity tests proper are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from hostsim import binding as H
+from lines import (GOLDENS, SEED, example_line, golden_two_machine, long50_line, mixed20_line, random_line,
+                   sweep10_line)
+from mjpdes_b200 import abi
+from parity import assert_same
+
+MODES = [abi.RNG_COUNTER, abi.RNG_REPLAY]
+KIND = {":up": 0, ":down": 1}
+
+
+@pytest.mark.parametrize("gid", ["G1", "G2"])
+def test_lazy_end_time_matches_reference_known_answers(gid):
+    g = GOLDENS[gid]
+    got = H.end_time([KIND[k] for _, k, _ in g["events"]], [t for _, _, t in g["events"]], g["clock"], g["dur"])
+    assert got == g["expected"]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_example_line(oracle, mode):
+    line = example_line(run_to=4000.0, warm_up=400.0)
+    assert_same(H.run(line, 6, mode=mode, seed=SEED), oracle.run(line, 6, mode=mode, seed=SEED).stats)
+
+
+@pytest.mark.parametrize("gid", ["G7", "G8", "G9"])
+def test_reference_two_machine_models(oracle, gid):
+    line = golden_two_machine(gid, lam=0.0, run_to=300.0)
+    assert_same(H.run(line, 2, mode=abi.RNG_REPLAY, seed=SEED), oracle.run(line, 2, mode=abi.RNG_REPLAY, seed=SEED).stats)
+
+
+@pytest.mark.parametrize("trial", range(16))
+def test_random_lines(oracle, trial):
+    rng = np.random.default_rng(1000 + trial)
+    M, K = int(rng.integers(2, 13)), int(rng.integers(1, 5))
+    line = random_line(rng, M, K, run_to=300.0, warm_up=30.0, jm2dm=bool(rng.random() < 0.3),
+                       up_down=bool(rng.random() < 0.4))
+    mode = MODES[trial % 2]
+    assert_same(H.run(line, 3, mode=mode, seed=trial), oracle.run(line, 3, mode=mode, seed=trial).stats)
+
+
+@pytest.mark.parametrize("M", [20, 33, 64])
+def test_wide_lines_use_64bit_masks(oracle, M):
+    line = random_line(np.random.default_rng(M), M, 3, run_to=120.0, warm_up=10.0)
+    assert_same(H.run(line, 2, seed=5), oracle.run(line, 2, seed=5).stats)
+
+
+def test_identical_machines_many_time_ties(oracle):
+    """38 % of ticks are genuine cross-machine time ties on a line of identical machines."""
+    line = abi.HostLine(lam=[.1] * 6, mu=[.9] * 6, W=[1.] * 6, discipline=[0, 1, 0, 1, 0, 0], N=[2] * 5,
+                        portion=[1.], w=[[1.] * 6], warm_up=50, run_to=1200)
+    for mode in MODES:
+        assert_same(H.run(line, 4, mode=mode, seed=3), oracle.run(line, 4, mode=mode, seed=3).stats)
+
+
+def test_named_configs(oracle):
+    for line, n in ((sweep10_line(5, warm_up=50, run_to=500, first=123456), 5),
+                    (mixed20_line(warm_up=50, run_to=300, log=False), 2),
+                    (long50_line(warm_up=50, run_to=250), 2)):
+        assert_same(H.run(line, n, seed=SEED), oracle.run(line, n, seed=SEED).stats)
+
+
+def test_jobtype_nil_status(oracle):
+    """p0 < p_{K-1} lets the draw fall off the shifted thresholds -> the reference dies."""
+    line = abi.HostLine(lam=[.1, .1], mu=[.9, .9], W=[1., 1.], discipline=[0, 0], N=[2], portion=[0.1, 0.2, 0.7],
+                        w=np.ones((3, 2)), warm_up=0, run_to=500)
+    a, b = H.run(line, 8, seed=1), oracle.run(line, 8, seed=1).stats
+    assert set(b.status.tolist()) == {abi.INST_JOBTYPE_NIL}
+    assert np.array_equal(a.status, b.status)
+
+
+def test_aggregate_matches_oracle(oracle):
+    line = example_line(run_to=1500.0, warm_up=100.0)
+    a, b = H.run(line, 7, seed=9), oracle.run(line, 7, seed=9).stats
+    assert a.aggregate[0] == 7
+    assert np.allclose(a.aggregate, b.aggregate, rtol=1e-12)
