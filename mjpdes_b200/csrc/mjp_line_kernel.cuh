@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
   __syncthreads();
 
   const uint64_t g = (uint64_t)blockIdx.x * nt + tid;
-  if (g >= p.n_inst) return;
   const uint64_t n_inst = p.n_inst;
+  // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
+  bool active = g < n_inst;
 
   // ---- per-thread state in shared memory: [slot][thread] -------------------
   double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
 
   // ---- preprocess-model: first up/down event of each machine (core.clj:156-160,557-562) ----
   MaskT up = 0;
-  for (int i = 0; i < M; ++i) {
+  for (int i = 0; active && i < M; ++i) {
     const double lam = lam_of(i), mu = mu_of(i);
     const double p_up = __ddiv_rn(mu, __dadd_rn(lam, mu));
     uint32_t o[4];
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
     SS(i) = QNAN;
     if (is_up) up |= MJP_BIT(i);
   }
-  for (int b = 0; b < M - 1; ++b) LASTCLK(b) = p.warm_up;
-  for (int q = 0; q < cntw; ++q) s_cnt[q * nt] = 0u;
+  for (int b = 0; active && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
+  for (int q = 0; active && q < cntw; ++q) s_cnt[q * nt] = 0u;
 
   // ---- model state in registers ---------------------------------------------
   double clock = 0.0;
@@ -272,62 +273,54 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
   };
 
   // ======================= main-loop-loop, core.clj:729-744 =======================
+  // One micro-step per trip, the warp in lock-step: without the explicit reconvergence point the
+  // lanes drift apart for good after the first divergent batch (ncu: 3.9 of 32 lanes per instruction).
   for (;;) {
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) do {
     // end-main-loop? core.clj:722-727
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
-      status = MJP_INST_NORMAL_END; break;
+      status = MJP_INST_NORMAL_END; active = false; break;
     }
-    if (++iters > p.max_iter) { status = MJP_INST_ITER_LIMIT; break; }
+    if (++iters > p.max_iter) { status = MJP_INST_ITER_LIMIT; active = false; break; }
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
     const MaskT c_aj = (~occ & ~B & up & (~bbs | notfull)) & (MaskT)1;                       // core.clj:343-354
     const MaskT c_tm = (up | upj) & ~(MaskT)1 & ~B & ~S & ~occ & nonempty & (~bbs | notfull) & ALL;   // core.clj:485-506
-    MaskT fin = ~occ;                                                                         // utils.clj:68-74
-    {
-      MaskT q = ~S & empty & occ & ~pend;
-      while (q) { const int i = MO::ffs(q); q &= q - 1; if (clock >= ENDS(i)) fin |= MJP_BIT(i); }
-    }
-    const MaskT c_st = ~S & empty & fin & ALL;                                                // core.clj:451-460
     const MaskT c_us = S & nonempty;                                                          // core.clj:462-470
     const MaskT c_ub = B & notfull & ALL;                                                     // core.clj:426-449
     const MaskT c_blb = bbs & ~B & ~occ & nonempty & full;     // BBS, time = clock          core.clj:387-394,406-411
     const MaskT c_bla = ~bbs & ~B & full & occ & ~pend & ALL;  // BAS, time = :ends          core.clj:376-383,401-405
     const MaskT c_tb = occ & ~B & notfull & ~pend & ALL;       // time = max(clock, :ends)   core.clj:472-483
-    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup) != 0;
+    const MaskT st_chk = ~S & empty & occ & ~pend;             // finished? needs clock >= :ends, utils.clj:68-74
 
-    // min over the timed candidates, remembering who attains it
+    // One fixed-trip pass over the machines (every lane does the same work): min over the timed
+    // candidates, remembering who attains it, and the finished? bits new-starved? needs.
     double tmin = INF;
-    MaskT m_ud = 0, m_tb = 0, m_bl = 0;
-    for (int i = 0; i < M; ++i) {                                                             // core.clj:356-372
-      const double t = FUT_T(i);
-      if (t < tmin) { tmin = t; m_ud = 0; }
-      if (t == tmin) m_ud |= MJP_BIT(i);
+    MaskT m_ud = 0, m_tb = 0, m_bl = 0, fin = ~occ;
+    for (int i = 0; i < M; ++i) {
+      const MaskT bit = MJP_BIT(i);
+      const double tf = FUT_T(i), en = ENDS(i);
+      if (tf < tmin) { tmin = tf; m_ud = m_tb = m_bl = 0; }                                   // core.clj:356-372
+      if (tf == tmin) m_ud |= bit;
+      const bool is_tb = (c_tb & bit) != 0, is_bl = (c_bla & bit) != 0;
+      const double tj = is_tb ? fmax(clock, en) : (is_bl ? en : INF);
+      if (tj < tmin) { tmin = tj; m_ud = m_tb = m_bl = 0; }
+      if (tj == tmin) { if (is_tb) m_tb |= bit; if (is_bl) m_bl |= bit; }
+      if ((st_chk & bit) && clock >= en) fin |= bit;
     }
     m_ud &= ~dup;
-    {
-      MaskT q = c_tb;
-      while (q) {
-        const int i = MO::ffs(q); q &= q - 1;
-        const double t = fmax(clock, ENDS(i));
-        if (t < tmin) { tmin = t; m_ud = m_tb = 0; }
-        if (t == tmin) m_tb |= MJP_BIT(i);
-      }
-      q = c_bla;
-      while (q) {
-        const int i = MO::ffs(q); q &= q - 1;
-        const double t = ENDS(i);
-        if (t < tmin) { tmin = t; m_ud = m_tb = m_bl = 0; }
-        if (t == tmin) m_bl |= MJP_BIT(i);
-      }
-    }
+    const MaskT c_st = ~S & empty & fin & ALL;                                                // core.clj:451-460
+    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup) != 0;
     double tstar = tmin;
     if (now_any) {
       if (clock < tmin) { tstar = clock; m_ud = m_tb = m_bl = 0; }
-      else if (clock > tmin) { status = MJP_INST_CLOCK_BACK; break; }                         // core.clj:133
+      else if (clock > tmin) { status = MJP_INST_CLOCK_BACK; active = false; break; }         // core.clj:133
     }
-    if (tstar == INF) { status = MJP_INST_NO_RUNABLES; break; }
-    if (clock > tstar) { status = MJP_INST_CLOCK_BACK; break; }
+    if (tstar == INF) { status = MJP_INST_NO_RUNABLES; active = false; break; }
+    if (clock > tstar) { status = MJP_INST_CLOCK_BACK; active = false; break; }
     const bool at_now = now_any;       // candidates at time `clock` are in the batch iff clock == tstar
     const MaskT b_aj = at_now ? c_aj : 0, b_tm = at_now ? c_tm : 0, b_st = at_now ? c_st : 0;
     const MaskT b_us = at_now ? c_us : 0, b_ub = at_now ? c_ub : 0;
@@ -357,7 +350,7 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
         const double choose = u53(o[0], o[1]);
         for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) { type = k; break; }
       }
-      if (type < 0) { status = MJP_INST_JOBTYPE_NIL; break; }
+      if (type < 0) { status = MJP_INST_JOBTYPE_NIL; active = false; break; }
       const uint32_t id = curjob + 1;
       start_job(0, type);
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
@@ -451,9 +444,11 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
       q = b_ub;
       while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_UB | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); B &= ~MJP_BIT(i); toggle(tgB_lo, tgB_hi, MJP_BIT(i)); }
     }
-    if (status == MJP_INST_TICK_OVERFLOW) break;
-    if (seen == 0) { status = MJP_INST_LOGBUF_EMPTY; break; }   // push-log returned nil, util/log.clj:95
+    if (status == MJP_INST_TICK_OVERFLOW) { active = false; break; }
+    if (seen == 0) { status = MJP_INST_LOGBUF_EMPTY; active = false; break; }   // push-log returned nil, util/log.clj:95
+    } while (0);
   }
+  if (g >= n_inst) return;
 
   // the reference never flushes the last tick: whatever is still in :log-buf is lost
   if (p.njobs) p.njobs[g] = njobs;

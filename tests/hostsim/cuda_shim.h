@@ -43,3 +43,8 @@ static inline unsigned long long atomicAdd(unsigned long long *a, unsigned long 
 using std::floor;
 using std::fmax;
 using std::fmin;
+// one thread per "warp": votes and warp barriers are the identity
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __any_sync(unsigned, int pred) { return pred; }
+static inline int __all_sync(unsigned, int pred) { return pred; }
+static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }
