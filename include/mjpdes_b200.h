@@ -115,8 +115,10 @@ typedef struct mjp_line_desc {
  * "the reference stream" is only definable per CONSUMER.  Consumers of one
  * instance: c=0 job type (one uniform per new-job); c=1+2i uniforms of machine i
  * (init up?/down? draw, then one `some-num` per sojourn); c=2+2i exponentials of
- * machine i.  Draw #idx of consumer c of instance g is
- *     Philox4x32-10(key = seed, counter = {idx, c, g_lo, g_hi}).
+ * machine i.  Draw #idx of consumer c of instance g is words (0,1) of
+ *     Philox4x32-10(key = seed, counter = {idx, c, g_lo, g_hi}),
+ * except for the job-type stream (c=0), which uses both halves of a block:
+ * draw #d is words (0,1) of block {d >> 1, 0, g} for even d, words (2,3) for odd d.
  *   MJP_RNG_COUNTER : sojourn n of a machine is Erlang-2, T = -ln(u1*u2)/rate,
  *                     from the four words of ONE Philox block {n, 1+2i, g};
  *                     distribution-identical to the loop at core.clj:185-191.

@@ -208,57 +208,58 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
   long long njobs = 0;
   int status = MJP_INST_NOT_RUN;
 
-  auto mark_seen = [&](int i) {       // (group-by :m) order, util/log.clj:44
+  int type_cache = -2;                 // job type of the NEXT job when already drawn (-2: not drawn)
+
+  auto mark_seen = [&](int i) {       // (group-by :m) order, util/log.clj:44 -- branch-free
     const MaskT bit = MJP_BIT(i);
-    if (!(seen & bit)) {
-      if (((seen >> 1) >> i) & 1) lead &= ~bit; else lead |= bit;
-      seen |= bit;
-    }
+    const MaskT fresh = bit & ~seen;                          // first message of machine i in this tick?
+    const MaskT next_seen = (MaskT)0 - (((seen >> 1) >> i) & 1);   // all-ones iff machine i+1 logged already
+    lead = (lead & ~fresh) | (fresh & ~next_seen);
+    seen |= bit;
   };
   auto toggle = [&](MaskT &lo, MaskT &hi, MaskT bit) {   // saturating 2-bit counter per machine
     const MaskT carry = lo & bit, sat = hi & lo & bit;
     lo = (lo ^ bit) | sat;
     hi |= carry;
   };
-  // push-log for the tick that just ended (util/log.clj:98-108): clean-log-buf + add-compute-log!
-  auto flush_tick = [&]() {
-    if (tick_clk >= p.warm_up) {                                           // util/log.clj:104
-      // :bl/:ub of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed in order
-      MaskT q = tgB_lo;
-      while (q) {
-        const int i = MO::ffs(q); q &= q - 1;
-        const double bs = BS(i);
-        if (((B0 >> i) & 1) && bs == bs) red_add(p.blocked + (size_t)i * n_inst + g, tick_clk - bs);   // block-
-        BS(i) = ((B >> i) & 1) ? tick_clk : QNAN;                                                       // block+
-      }
-      q = tgS_lo;
-      while (q) {
-        const int i = MO::ffs(q); q &= q - 1;
-        const double ss = SS(i);
-        if (((S0 >> i) & 1) && ss == ss) red_add(p.starved + (size_t)i * n_inst + g, tick_clk - ss);   // starve-
-        SS(i) = ((S >> i) & 1) ? tick_clk : QNAN;                                                       // starve+
-      }
-      // buf+ / buf- (util/log.clj:159-171): the first message on a buffer in cleaned order gets the
-      // elapsed time, the others add (clk - clk) = 0.
-      q = has_bj | has_sm;
-      while (q) {
-        const int b = MO::ffs(q); q &= q - 1;
-        const int cf = (int)getb(s_cnt, b);
-        const bool bj = (has_bj >> b) & 1, sm = (has_sm >> b) & 1;
-        int n;
-        if (bj && !sm) n = cf - 1;
-        else if (sm && !bj) n = cf + 1;
-        else {
-          const bool bj_first_rt = (rtbj >> b) & 1;
-          const int n_bj = bj_first_rt ? cf : cf - 1, n_sm = bj_first_rt ? cf + 1 : cf;
-          n = ((lead >> b) & 1) ? n_bj : n_sm;        // machine b logged before machine b+1 in this tick?
-        }
-        const double lc = LASTCLK(b);
-        red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
-        LASTCLK(b) = tick_clk;
-      }
-      if (has_ej) { residence = residence + (tick_clk - ej_ent); njobs++; }   // end-job util/log.clj:212-217
+  // new-job (core.clj:328-340): job number d+1 uses half (d & 1) of Philox block {d >> 1, consumer 0}
+  auto type_from = [&](double choose) -> int {
+    for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) return k;
+    return -1;
+  };
+  // push-log for the tick that just ended (util/log.clj:98-108): clean-log-buf + add-compute-log!.
+  // Entered by the lanes of `fm`; its three loops are voted over `fm` so the lanes stay together.
+  auto flush_tick = [&](const unsigned fm) {
+    const bool warm = tick_clk >= p.warm_up;                               // util/log.clj:104
+    // :bl/:ub of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed in order
+    for (MaskT q = warm ? tgB_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
+      const int i = MO::ffs(q); q &= q - 1;
+      const double bs = BS(i);
+      if (((B0 >> i) & 1) && bs == bs) red_add(p.blocked + (size_t)i * n_inst + g, tick_clk - bs);   // block-
+      BS(i) = ((B >> i) & 1) ? tick_clk : QNAN;                                                       // block+
     }
+    for (MaskT q = warm ? tgS_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
+      const int i = MO::ffs(q); q &= q - 1;
+      const double ss = SS(i);
+      if (((S0 >> i) & 1) && ss == ss) red_add(p.starved + (size_t)i * n_inst + g, tick_clk - ss);   // starve-
+      SS(i) = ((S >> i) & 1) ? tick_clk : QNAN;                                                       // starve+
+    }
+    // buf+ / buf- (util/log.clj:159-171): the first message on a buffer in cleaned order gets the
+    // elapsed time, the others add (clk - clk) = 0.
+    for (MaskT q = warm ? (has_bj | has_sm) : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
+      const int b = MO::ffs(q); q &= q - 1;
+      const int cf = (int)getb(s_cnt, b);
+      const bool bj = (has_bj >> b) & 1, sm = (has_sm >> b) & 1, bj_first_rt = (rtbj >> b) & 1;
+      // levels seen by the :bj and the :sm of this tick, from the final count cf
+      const int n_bj = sm ? (bj_first_rt ? cf : cf - 1) : cf - 1;
+      const int n_sm = bj ? (bj_first_rt ? cf + 1 : cf) : cf + 1;
+      const bool take_bj = bj && (!sm || ((lead >> b) & 1));   // machine b logged before machine b+1?
+      const int n = take_bj ? n_bj : n_sm;
+      const double lc = LASTCLK(b);
+      red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
+      LASTCLK(b) = tick_clk;
+    }
+    if (warm && has_ej) { residence = residence + (tick_clk - ej_ent); njobs++; }   // end-job util/log.clj:212-217
     seen = lead = has_bj = has_sm = rtbj = 0;
     tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
     has_ej = false;
@@ -273,17 +274,19 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
   };
 
   // ======================= main-loop-loop, core.clj:729-744 =======================
-  // One micro-step per trip, the warp in lock-step: without the explicit reconvergence point the
-  // lanes drift apart for good after the first divergent batch (ncu: 3.9 of 32 lanes per instruction).
+  // One micro-step per trip with the warp in lock-step.  Nothing leaves the body early: a lane that
+  // ends (or errs) empties its batch and rides along to the bottom, so every section can be a loop
+  // voted over `am` (__any_sync is the reconvergence point; ncu showed 3.9 of 32 lanes per
+  // instruction without it).
   for (;;) {
-    __syncwarp();
-    if (!__any_sync(0xffffffffu, active)) break;
-    if (active) do {
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    if (am == 0) break;
+    if (active) {
+    bool live = true;
     // end-main-loop? core.clj:722-727
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
-      status = MJP_INST_NORMAL_END; active = false; break;
-    }
-    if (++iters > p.max_iter) { status = MJP_INST_ITER_LIMIT; active = false; break; }
+      status = MJP_INST_NORMAL_END; live = false;
+    } else if (++iters > p.max_iter) { status = MJP_INST_ITER_LIMIT; live = false; }
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -317,63 +320,75 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
     double tstar = tmin;
     if (now_any) {
       if (clock < tmin) { tstar = clock; m_ud = m_tb = m_bl = 0; }
-      else if (clock > tmin) { status = MJP_INST_CLOCK_BACK; active = false; break; }         // core.clj:133
+      else if (clock > tmin && live) { status = MJP_INST_CLOCK_BACK; live = false; }          // core.clj:133
     }
-    if (tstar == INF) { status = MJP_INST_NO_RUNABLES; active = false; break; }
-    if (clock > tstar) { status = MJP_INST_CLOCK_BACK; active = false; break; }
-    const bool at_now = now_any;       // candidates at time `clock` are in the batch iff clock == tstar
-    const MaskT b_aj = at_now ? c_aj : 0, b_tm = at_now ? c_tm : 0, b_st = at_now ? c_st : 0;
-    const MaskT b_us = at_now ? c_us : 0, b_ub = at_now ? c_ub : 0;
-    const MaskT b_bl = m_bl | (at_now ? c_blb : 0);
-    const MaskT b_ud = m_ud | (at_now ? dup : 0);
-    const MaskT b_up = b_ud & ~up, b_dn = b_ud & up;
-    const MaskT b_tb = m_tb;
+    if (live && tstar == INF) { status = MJP_INST_NO_RUNABLES; live = false; }
+    if (live && clock > tstar) { status = MJP_INST_CLOCK_BACK; live = false; }
+    // candidates at time `clock` are in the batch iff clock == tstar, i.e. iff now_any
+    const MaskT keep_now = (live && now_any) ? ~(MaskT)0 : (MaskT)0, keep = live ? ~(MaskT)0 : (MaskT)0;
+    MaskT b_aj = c_aj & keep_now;
+    MaskT b_tm = c_tm & keep_now, b_st = c_st & keep_now, b_us = c_us & keep_now, b_ub = c_ub & keep_now;
+    MaskT b_bl = (m_bl & keep) | (c_blb & keep_now);
+    MaskT b_ud = (m_ud & keep) | (dup & keep_now);
+    MaskT b_tb = m_tb & keep;
 
     // ---- advance-clock core.clj:128-135 ----
-    if (tstar != clock) fired = 0;
-    clock = tstar;
-    const bool will_log = p.up_down ? true : ((b_aj | b_tb | b_tm | b_st | b_us | b_bl | b_ub) != 0);
-    if (will_log) {
-      if (seen != 0 && clock != tick_clk) flush_tick();       // push-log of the previous tick
-      tick_clk = clock;
+    if (live) {
+      if (tstar != clock) fired = 0;
+      clock = tstar;
+    }
+    const bool will_log = live && (p.up_down ? true : ((b_aj | b_tb | b_tm | b_st | b_us | b_bl | b_ub) != 0));
+    {
+      const bool do_flush = will_log && seen != 0 && clock != tick_clk;   // push-log of the previous tick
+      const unsigned fm = __ballot_sync(am, do_flush);
+      if (do_flush) flush_tick(fm);
+      if (will_log) tick_clk = clock;
     }
     n_events += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
                 MO::popc(b_us) + MO::popc(b_bl) + MO::popc(b_ub);
 
     // ---- run the batch in generator order, core.clj:742 ----
-    if (b_aj) {                                              // add-job core.clj:240-254, new-job core.clj:328-340
-      int type = -1;
-      if (K == 1 && c_thr[0] >= 1.0) type = 0;
-      else {
-        uint32_t o[4];
-        philox4x32_10(curjob, 0u, g_lo, g_hi, k0, k1, o);
-        const double choose = u53(o[0], o[1]);
-        for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) { type = k; break; }
+    if (__any_sync(am, b_aj != 0)) {
+      if (b_aj) {                                            // add-job core.clj:240-254, new-job core.clj:328-340
+        int type;
+        if (K == 1 && c_thr[0] >= 1.0) type = 0;
+        else if (type_cache != -2) { type = type_cache; type_cache = -2; }
+        else {
+          uint32_t o[4];
+          philox4x32_10(curjob >> 1, 0u, g_lo, g_hi, k0, k1, o);
+          if (curjob & 1) type = type_from(u53(o[2], o[3]));
+          else { type = type_from(u53(o[0], o[1])); type_cache = type_from(u53(o[2], o[3])); }
+        }
+        if (type < 0) {                                      // the reference dies in job-requires
+          status = MJP_INST_JOBTYPE_NIL; live = false;
+          b_ud = b_tb = b_tm = b_st = b_us = b_bl = b_ub = 0;
+        } else {
+          const uint32_t id = curjob + 1;
+          start_job(0, type);
+          if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
+          mark_seen(0);
+          curjob = id; occ |= 1; STARTED(0) = id;
+          setb(s_jt, (int)(id & Rm), (uint32_t)type);
+          p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
+          if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
+        }
       }
-      if (type < 0) { status = MJP_INST_JOBTYPE_NIL; active = false; break; }
-      const uint32_t id = curjob + 1;
-      start_job(0, type);
-      if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
-      mark_seen(0);
-      curjob = id; occ |= 1; STARTED(0) = id;
-      setb(s_jt, (int)(id & Rm), (uint32_t)type);
-      p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
-      if (fired & 1) { dup |= 1; up ^= 1; }                  // machine-future core.clj:194-198
     }
-    {                                                        // bring-machine-up / -down core.clj:215-238
-      MaskT q = b_up;
-      for (int pass = 0; pass < 2; ++pass) {
-        while (q) {
-          const int i = MO::ffs(q); q &= q - 1;
-          const MaskT bit = MJP_BIT(i);
-          const bool was_up_event = !(up & bit);
-          if (HASH) {
-            hmix(h, (uint64_t)(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN) | ((uint64_t)i << 8));
-            hmix(h, d2bits(clock)); hmix(h, 0);
-          }
-          if (p.up_down) mark_seen(i);
-          fired |= bit;
-          if (dup & bit) { dup &= ~bit; up ^= bit; continue; }       // re-fire of an already realised event
+    {                                                        // bring-machine-up, then -down: core.clj:215-238
+      MaskT q_up = b_ud & ~up, q_dn = b_ud & up;
+      while (__any_sync(am, (q_up | q_dn) != 0)) if (q_up | q_dn) {
+        MaskT &q = q_up ? q_up : q_dn;
+        const int i = MO::ffs(q); q &= q - 1;
+        const MaskT bit = MJP_BIT(i);
+        const bool was_up_event = !(up & bit);
+        if (HASH) {
+          hmix(h, (uint64_t)(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN) | ((uint64_t)i << 8));
+          hmix(h, d2bits(clock)); hmix(h, 0);
+        }
+        if (p.up_down) mark_seen(i);
+        fired |= bit;
+        if (dup & bit) { dup &= ~bit; up ^= bit; }           // re-fire of an already realised event
+        else {
           const double t_fire = FUT_T(i);
           const uint32_t n = FUT_N(i);
           const double t_next = next_event_time(i, n, was_up_event, t_fire);
@@ -384,69 +399,66 @@ __global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
             ENDS(i) = v;
           }
         }
-        q = b_dn;
       }
     }
-    {                                                        // advance2buffer core.clj:285-300
-      MaskT q = b_tb;
-      while (q) {
+    for (MaskT q = b_tb; __any_sync(am, q != 0);) if (q) {   // advance2buffer core.clj:285-300
+      const int i = MO::ffs(q); q &= q - 1;
+      const MaskT bit = MJP_BIT(i);
+      const uint32_t id = STARTED(i);
+      if (i < M - 1) {
+        const int n = (int)getb(s_cnt, i);
+        if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ENDS(i))); }
+        mark_seen(i);
+        if (has_bj & bit) status = MJP_INST_TICK_OVERFLOW;
+        has_bj |= bit;
+        rtbj |= bit & ~has_sm;
+        setb(s_cnt, i, (uint32_t)(n + 1));
+        if (n + 1 == cap_of(i)) full |= bit;
+        empty &= ~(bit << 1);
+      } else {
+        const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
+        if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(ENDS(i))); }
+        mark_seen(i);
+        if (has_ej) status = MJP_INST_TICK_OVERFLOW;
+        has_ej = true; ej_ent = ent;
+      }
+      occ &= ~bit;
+    }
+    for (MaskT q = b_tm; __any_sync(am, q != 0);) if (q) {   // advance2machine core.clj:263-277
+      const int i = MO::ffs(q); q &= q - 1;
+      const MaskT bit = MJP_BIT(i), bbit = bit >> 1;
+      const int b = i - 1;
+      const int n = (int)getb(s_cnt, b);
+      const uint32_t id = STARTED(i) + 1;
+      const int type = (int)getb(s_jt, (int)(id & Rm));
+      start_job(i, type);
+      if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
+      mark_seen(i);
+      if (has_sm & bbit) status = MJP_INST_TICK_OVERFLOW;
+      has_sm |= bbit;
+      setb(s_cnt, b, (uint32_t)(n - 1));
+      if (n - 1 == 0) empty |= bit;
+      full &= ~bbit;
+      occ |= bit; STARTED(i) = id;
+      if (fired & bit) { dup |= bit; up ^= bit; }
+    }
+    {                                                        // record-actions core.clj:304-326, in the order
+      MaskT q_st = b_st, q_us = b_us, q_bl = b_bl, q_ub = b_ub;   // new-starved, -unstarved, -blocked, -unblocked
+      while (__any_sync(am, (q_st | q_us | q_bl | q_ub) != 0)) if (q_st | q_us | q_bl | q_ub) {
+        const int which = q_st ? 0 : (q_us ? 1 : (q_bl ? 2 : 3));
+        MaskT &q = which == 0 ? q_st : (which == 1 ? q_us : (which == 2 ? q_bl : q_ub));
         const int i = MO::ffs(q); q &= q - 1;
         const MaskT bit = MJP_BIT(i);
-        const uint32_t id = STARTED(i);
-        if (i < M - 1) {
-          const int n = (int)getb(s_cnt, i);
-          if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ENDS(i))); }
-          mark_seen(i);
-          if (has_bj & bit) status = MJP_INST_TICK_OVERFLOW;
-          has_bj |= bit;
-          if (!(has_sm & bit)) rtbj |= bit;
-          setb(s_cnt, i, (uint32_t)(n + 1));
-          if (n + 1 == cap_of(i)) full |= bit;
-          empty &= ~(bit << 1);
-        } else {
-          const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
-          if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(ENDS(i))); }
-          mark_seen(i);
-          if (has_ej) status = MJP_INST_TICK_OVERFLOW;
-          has_ej = true; ej_ent = ent;
-        }
-        occ &= ~bit;
-      }
-    }
-    {                                                        // advance2machine core.clj:263-277
-      MaskT q = b_tm;
-      while (q) {
-        const int i = MO::ffs(q); q &= q - 1;
-        const MaskT bit = MJP_BIT(i), bbit = bit >> 1;
-        const int b = i - 1;
-        const int n = (int)getb(s_cnt, b);
-        const uint32_t id = STARTED(i) + 1;
-        const int type = (int)getb(s_jt, (int)(id & Rm));
-        start_job(i, type);
-        if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
+        if (HASH) { hmix(h, (uint64_t)(MJP_ACT_ST + which) | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); }
         mark_seen(i);
-        if (has_sm & bbit) status = MJP_INST_TICK_OVERFLOW;
-        has_sm |= bbit;
-        setb(s_cnt, b, (uint32_t)(n - 1));
-        if (n - 1 == 0) empty |= bit;
-        full &= ~bbit;
-        occ |= bit; STARTED(i) = id;
-        if (fired & bit) { dup |= bit; up ^= bit; }
+        if (which < 2) { S ^= bit; toggle(tgS_lo, tgS_hi, bit); }
+        else { B ^= bit; toggle(tgB_lo, tgB_hi, bit); }
       }
     }
-    {                                                        // record-actions core.clj:304-326
-      MaskT q = b_st;
-      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_ST | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); S |= MJP_BIT(i); toggle(tgS_lo, tgS_hi, MJP_BIT(i)); }
-      q = b_us;
-      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_US | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); S &= ~MJP_BIT(i); toggle(tgS_lo, tgS_hi, MJP_BIT(i)); }
-      q = b_bl;
-      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_BL | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); B |= MJP_BIT(i); toggle(tgB_lo, tgB_hi, MJP_BIT(i)); }
-      q = b_ub;
-      while (q) { const int i = MO::ffs(q); q &= q - 1; if (HASH) { hmix(h, (uint64_t)MJP_ACT_UB | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); } mark_seen(i); B &= ~MJP_BIT(i); toggle(tgB_lo, tgB_hi, MJP_BIT(i)); }
+    if (status == MJP_INST_TICK_OVERFLOW) live = false;
+    else if (live && seen == 0) { status = MJP_INST_LOGBUF_EMPTY; live = false; }   // push-log returned nil, util/log.clj:95
+    active = live;
     }
-    if (status == MJP_INST_TICK_OVERFLOW) { active = false; break; }
-    if (seen == 0) { status = MJP_INST_LOGBUF_EMPTY; active = false; break; }   // push-log returned nil, util/log.clj:95
-    } while (0);
   }
   if (g >= n_inst) return;
 

@@ -374,7 +374,10 @@ struct Sim {
 
   /* new-job, core:328-340 (thresholds p0, 2p0, 2p0+p1, ... : SURVEY Q4) */
   Job new_job() {
-    double choose = draws.uniform(0, jt_idx++);
+    /* draw #d of consumer 0 is half (d & 1) of Philox block {d >> 1, 0} (include/mjpdes_b200.h) */
+    uint32_t d = jt_idx++, o[4];
+    draws.block(0, d >> 1, o);
+    double choose = (d & 1) ? Draws::u53(o[2], o[3]) : Draws::u53(o[0], o[1]);
     int type = -1;
     double accum = portion[0];
     for (int k = 0; k < K; ++k) {
