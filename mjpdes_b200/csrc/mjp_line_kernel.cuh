@@ -71,7 +71,7 @@ __device__ __forceinline__ bool end_time_resume(double t_up, double t_down, doub
 #define MJP_BIT(i) ((MaskT)1 << (i))
 
 template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP>
-__global__ void __launch_bounds__(256) mjp_line_kernel(const KParams p) {
+__global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x, M = p.M, K = p.K;

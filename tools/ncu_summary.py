@@ -26,7 +26,7 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
 for k in keys:
     if k in m:
         print(f"{k:85s} {m[k][0]} {m[k][1]}")
-wi = float(m["smsp__inst_executed.sum"][0]); ti = float(m["smsp__thread_inst_executed.sum"][0])
+wi = float(m["smsp__inst_executed.sum"][0]); ti = wi * float(m["smsp__thread_inst_executed_per_inst_executed.ratio"][0])
 ce = float(m["smsp__cycles_elapsed.sum"][0])
 print(f"issue-slot utilisation (inst_executed / cycles_elapsed) {wi / ce:.4f}")
 print(f"lane efficiency (thread_inst / 32 inst)               {ti / (32 * wi):.4f}")
