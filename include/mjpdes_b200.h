@@ -207,6 +207,8 @@ int mjp_run(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst,
 /* Device-resident variant used for measurement: upload once, run many times,
  * download when wanted.  mjp_run() == upload + launch + sync + download.       */
 int mjp_upload(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst);
+/* device buffer for SCADA records (needed before a launch with want_log); mjp_run() does it itself */
+int mjp_reserve_log(mjp_handle *h, uint64_t capacity);
 int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log);  /* async on the handle's stream */
 int mjp_sync(mjp_handle *h);
 int mjp_download(mjp_handle *h, mjp_stats_out *stats, mjp_log_out *log);

@@ -238,6 +238,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.mjp_run.argtypes = [H, C.POINTER(LineDesc), C.c_uint64, C.POINTER(RngSpec), C.POINTER(StatsOut),
                             C.POINTER(LogOut)]
     lib.mjp_upload.argtypes = [H, C.POINTER(LineDesc), C.c_uint64]
+    lib.mjp_reserve_log.argtypes = [H, C.c_uint64]
     lib.mjp_launch.argtypes = [H, C.POINTER(RngSpec), C.c_int]
     lib.mjp_sync.argtypes = [H]
     lib.mjp_download.argtypes = [H, C.POINTER(StatsOut), C.POINTER(LogOut)]
@@ -253,6 +254,6 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "mjp_abi_version", "mjp_device_count", "mjp_aggregate_len", "mjp_create", "mjp_destroy", "mjp_last_error",
-    "mjp_run", "mjp_upload", "mjp_launch", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
+    "mjp_run", "mjp_upload", "mjp_reserve_log", "mjp_launch", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
     "mjp_last_launch_count", "mjp_probe_end_time",
 ]

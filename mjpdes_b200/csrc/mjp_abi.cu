@@ -77,17 +77,6 @@ static int fail(mjp_handle *h, int code, const char *msg) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-namespace mjp {
-// SCADA capture path (filled in by the log kernel)
-static int reserve_log(mjp_handle *h, uint64_t capacity) {
-  (void)capacity;
-  return fail(h, MJP_ERR_UNSUPPORTED, "SCADA log capture is not available in this build");
-}
-static int launch_log_path(mjp_handle *h, bool, bool, int *) {
-  return fail(h, MJP_ERR_UNSUPPORTED, "SCADA log capture is not available in this build");
-}
-}  // namespace mjp
-
 /* the checks of core.clj:75-121 (clojure.spec) that concern the loop, plus the kernel's own limits */
 static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   if (!L) return fail(h, MJP_ERR_INVALID, "line descriptor is NULL");
@@ -129,9 +118,9 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   return MJP_OK;
 }
 
-template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP>
+template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
 static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int threads, size_t smem, cudaStream_t st) {
-  auto k = mjp::mjp_line_kernel<MaskT, REPLAY, HASH, SWEEP>;
+  auto k = mjp::mjp_line_kernel<MaskT, REPLAY, HASH, SWEEP, LOG>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<blocks, threads, smem, st>>>(kp);
@@ -139,19 +128,17 @@ static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int thread
 }
 
 template <typename MaskT>
-static cudaError_t launch_mask(bool replay, bool hash, bool sweep, const mjp::KParams &kp, int blocks, int threads,
-                               size_t smem, cudaStream_t st) {
-  const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
+static cudaError_t launch_mask(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
+                               int threads, size_t smem, cudaStream_t st) {
+  const int v = (log ? 8 : 0) | (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
+#define MJP_CASE(n) \
+  case n: return launch_variant<MaskT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, ((n) & 8) != 0>(kp, blocks, threads, smem, st);
   switch (v) {
-    case 0: return launch_variant<MaskT, false, false, false>(kp, blocks, threads, smem, st);
-    case 1: return launch_variant<MaskT, false, false, true>(kp, blocks, threads, smem, st);
-    case 2: return launch_variant<MaskT, false, true, false>(kp, blocks, threads, smem, st);
-    case 3: return launch_variant<MaskT, false, true, true>(kp, blocks, threads, smem, st);
-    case 4: return launch_variant<MaskT, true, false, false>(kp, blocks, threads, smem, st);
-    case 5: return launch_variant<MaskT, true, false, true>(kp, blocks, threads, smem, st);
-    case 6: return launch_variant<MaskT, true, true, false>(kp, blocks, threads, smem, st);
-    default: return launch_variant<MaskT, true, true, true>(kp, blocks, threads, smem, st);
+    MJP_CASE(0) MJP_CASE(1) MJP_CASE(2) MJP_CASE(3) MJP_CASE(4) MJP_CASE(5) MJP_CASE(6) MJP_CASE(7)
+    MJP_CASE(8) MJP_CASE(9) MJP_CASE(10) MJP_CASE(11) MJP_CASE(12) MJP_CASE(13) MJP_CASE(14)
+    default: return launch_variant<MaskT, true, true, true, true>(kp, blocks, threads, smem, st);
   }
+#undef MJP_CASE
 }
 
 extern "C" {
@@ -292,8 +279,20 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   CK(h->d_partials.reserve((size_t)h->agg_blocks * len * 8));
   CK(h->d_agg.reserve((size_t)len * 8));
   CK(h->d_logcur.reserve(16));
+  kp.log_cursor = h->d_logcur.as<unsigned long long>();
   CK(cudaStreamSynchronize(h->stream));
   h->uploaded = true;
+  return MJP_OK;
+}
+
+int mjp_reserve_log(mjp_handle *h, uint64_t capacity) {
+  if (!h) return MJP_ERR_INVALID;
+  if (!h->uploaded) return fail(h, MJP_ERR_INVALID, "mjp_reserve_log before mjp_upload");
+  CK(cudaSetDevice(h->device));
+  CK(h->d_log.reserve((capacity ? capacity : 1) * sizeof(mjp_log_record)));
+  h->kp.log_records = h->d_log.ptr;
+  h->kp.log_capacity = capacity;
+  h->kp.log_cursor = h->d_logcur.as<unsigned long long>();
   return MJP_OK;
 }
 
@@ -313,15 +312,13 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
   CK(cudaMemsetAsync(h->d_logcur.ptr, 0, 16, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   const bool replay = rng->mode == MJP_RNG_REPLAY, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
-  if (h->want_log) {
-    int rc = mjp::launch_log_path(h, replay, hash, &launches);
-    if (rc != MJP_OK) return rc;
-  } else {
+  if (h->want_log && !kp.log_records) return fail(h, MJP_ERR_INVALID, "SCADA capture wanted: call mjp_reserve_log first");
+  {
     const int threads = h->block_threads;
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
     cudaError_t e = (kp.M <= 32)
-        ? launch_mask<uint32_t>(replay, hash, h->sweep, kp, blocks, threads, h->smem_bytes, h->stream)
-        : launch_mask<uint64_t>(replay, hash, h->sweep, kp, blocks, threads, h->smem_bytes, h->stream);
+        ? launch_mask<uint32_t>(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream)
+        : launch_mask<uint64_t>(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream);
     CK(e);
     launches++;
   }
@@ -400,7 +397,7 @@ int mjp_run(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst, const mjp
   int rc = mjp_upload(h, line, n_inst);
   if (rc != MJP_OK) return rc;
   if (log && line->log) {
-    rc = mjp::reserve_log(h, log->capacity);
+    rc = mjp_reserve_log(h, log->capacity);
     if (rc != MJP_OK) return rc;
   }
   rc = mjp_launch(h, rng, log != nullptr);

@@ -70,7 +70,7 @@ __device__ __forceinline__ bool end_time_resume(double t_up, double t_down, doub
 
 #define MJP_BIT(i) ((MaskT)1 << (i))
 
-template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP>
+template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
 __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,21 +140,20 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
   const double QNAN = __longlong_as_double(0x7FF8000000000000ll);
 
   // sojourn after the event (kind_was_up ? :up : :down) numbered n_prev at time t_prev  (core.clj:180-191)
-  auto next_event_time = [&](int i, uint32_t n_prev, bool prev_is_up, double t_prev) -> double {
+  // `e` is the machine's cursor in its exponential stream (REPLAY only); the caller decides whether to commit it.
+  auto next_event_time = [&](int i, uint32_t n_prev, bool prev_is_up, double t_prev, uint32_t &e) -> double {
     const double rate = prev_is_up ? lam_of(i) : mu_of(i);
     uint32_t o[4];
     double T;
     if (REPLAY) {
       philox4x32_10(n_prev + 1, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
       const double some_num = u53(o[0], o[1]);                                   // core.clj:185
-      uint32_t e = s_eidx[i * nt];
       philox4x32_10(e++, 2u + 2u * i, g_lo, g_hi, k0, k1, o);
       T = __ddiv_rn(-det_log(u52open(o[0], o[1])), rate);                        // core.clj:187
       while (!(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {      // core.clj:188, 162-165
         philox4x32_10(e++, 2u + 2u * i, g_lo, g_hi, k0, k1, o);
         T = __dadd_rn(T, __ddiv_rn(-det_log(u52open(o[0], o[1])), rate));        // core.clj:190-191
       }
-      s_eidx[i * nt] = e;
     } else {
       philox4x32_10(n_prev + 1, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
       T = __ddiv_rn(-det_log(__dmul_rn(u52open(o[0], o[1]), u52open(o[2], o[3]))), rate);   // Erlang-2
@@ -227,6 +226,90 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
     for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) return k;
     return -1;
   };
+  // ---- SCADA capture (LOG): :log-buf of the current tick, staged in shared memory ----
+  // word: act | m << 8 | n << 16 | done << 31 | job << 32
+  unsigned long long *s_stage = reinterpret_cast<unsigned long long *>(sf + (size_t)(5 * M - 1) * nt);
+  uint32_t *s_ord = s_eidx + (size_t)M * nt;               // cleaned order, 4 indices per word
+  const int stage_cap = p.stage_cap;
+  int n_staged = 0;
+  uint32_t line_cnt = 0;                                   // [:report :line-cnt]
+  double aj_ends = 0.0;
+  auto stage_msg = [&](int act, int m, int n, uint32_t job) {      // log/log util/log.clj:30-36
+    if (n_staged < stage_cap)
+      s_stage[n_staged * nt] = (unsigned long long)act | ((unsigned long long)m << 8) |
+                               ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);
+    else status = MJP_INST_TICK_OVERFLOW;
+    n_staged++;
+  };
+  // clean-log-buf (util/log.clj:38-57) + print-lines (util/log.clj:111-137): order the staged messages,
+  // reserve space with ONE atomicAdd per warp, write 32-byte records.
+  auto emit_tick = [&](const unsigned fm) {
+    const int lane = tid & 31;
+    const int ns = n_staged < stage_cap ? n_staged : stage_cap;
+    const bool print_now = p.log_on && tick_clk >= p.warm_up && p.max_lines > (uint64_t)line_cnt;   // util/log.clj:220-226
+    int k = 0;
+    if (print_now) {
+      for (int a = 0; a < ns; ++a) {
+        const unsigned long long wa = s_stage[a * nt];
+        if (wa & (1ull << 31)) continue;
+        const int m = (int)((wa >> 8) & 0xFF);                 // next machine in (group-by :m) order
+        int cnt[3] = {0, 0, 0}, order[3], no = 0;
+        for (int b = a; b < ns; ++b) {
+          const unsigned long long wb = s_stage[b * nt];
+          if ((int)((wb >> 8) & 0xFF) != m) continue;
+          const int act = (int)(wb & 0xFF);
+          const int c = (act == MJP_ACT_BL || act == MJP_ACT_UB) ? 0 : ((act == MJP_ACT_ST || act == MJP_ACT_US) ? 1 : 2);
+          if (cnt[c]++ == 0) order[no++] = c;
+        }
+        for (int q = 0; q < no; ++q) {
+          const int c = order[q];
+          const bool drop = (c < 2) && cnt[c] == 2;            // util/log.clj:51-53
+          for (int b = a; b < ns; ++b) {
+            const unsigned long long wb = s_stage[b * nt];
+            if ((int)((wb >> 8) & 0xFF) != m) continue;
+            const int act = (int)(wb & 0xFF);
+            const int cc = (act == MJP_ACT_BL || act == MJP_ACT_UB) ? 0 : ((act == MJP_ACT_ST || act == MJP_ACT_US) ? 1 : 2);
+            if (cc != c) continue;
+            s_stage[b * nt] = wb | (1ull << 31);
+            if (!drop) { setb(s_ord, k, (uint32_t)b); ++k; }
+          }
+        }
+      }
+    }
+    // warp-aggregated reservation over the lanes that flush in this micro-step
+    unsigned prefix = 0, total = 0;
+    for (unsigned rest = fm; rest;) {
+      const int src = __ffs((int)rest) - 1; rest &= rest - 1;
+      const unsigned v = __shfl_sync(fm, (unsigned)k, src);
+      if (src < lane) prefix += v;
+      total += v;
+    }
+    unsigned long long base = 0;
+    const int leader = __ffs((int)fm) - 1;
+    if (lane == leader && total) base = atomicAdd(p.log_cursor, (unsigned long long)total);
+    base = __shfl_sync(fm, base, leader);
+    if (k) {
+      mjp_log_record *out = reinterpret_cast<mjp_log_record *>(p.log_records);
+      unsigned dropped = 0;
+      for (int q = 0; q < k; ++q) {
+        const unsigned long long w = s_stage[getb(s_ord, q) * nt];
+        const unsigned long long at = base + prefix + q;
+        if (at >= p.log_capacity) { ++dropped; continue; }
+        const int act = (int)(w & 0xFF);
+        const double aux = act == MJP_ACT_AJ ? aj_ends : (act == MJP_ACT_EJ ? ej_ent : QNAN);
+        // two 16-byte stores = one full 32-byte sector per record
+        const unsigned long long w2 = (unsigned long long)(uint32_t)(w >> 32) | ((unsigned long long)(uint32_t)g << 32);
+        const unsigned long long w3 = (unsigned long long)(line_cnt + q) | (((w >> 16) & 0x7FFFull) << 32) |
+                                      ((w & 0xFFull) << 48) | (((w >> 8) & 0xFFull) << 56);
+        double2 *dst = reinterpret_cast<double2 *>(out + at);
+        dst[0] = make_double2(tick_clk, aux);
+        dst[1] = make_double2(__longlong_as_double((long long)w2), __longlong_as_double((long long)w3));
+      }
+      if (dropped) atomicAdd(p.log_cursor + 1, (unsigned long long)dropped);
+      line_cnt += (uint32_t)k;                               // util/log.clj:137
+    }
+    n_staged = 0;
+  };
   // push-log for the tick that just ended (util/log.clj:98-108): clean-log-buf + add-compute-log!.
   // Entered by the lanes of `fm`; its three loops are voted over `fm` so the lanes stay together.
   auto flush_tick = [&](const unsigned fm) {
@@ -260,6 +343,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
       LASTCLK(b) = tick_clk;
     }
     if (warm && has_ej) { residence = residence + (tick_clk - ej_ent); njobs++; }   // end-job util/log.clj:212-217
+    if (LOG) emit_tick(fm);
     seen = lead = has_bj = has_sm = rtbj = 0;
     tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
     has_ej = false;
@@ -367,6 +451,24 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
           start_job(0, type);
           if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
           mark_seen(0);
+          if (LOG) {
+            stage_msg(MJP_ACT_AJ, 0, type, id);
+            // the :aj record carries :ends (core.clj:250): when the lazy end-time is still pending, run the
+            // literal look-ahead of core.clj:141-151 over events that are generated but not committed
+            if (!(pend & 1)) aj_ends = ENDS(0);
+            else {
+              double rem = ENDS(0), t = FUT_T(0), v;
+              uint32_t n = FUT_N(0), ecur = REPLAY ? s_eidx[0] : 0u;
+              if (up & 1) { t = next_event_time(0, n, false, t, ecur); ++n; }      // the :up after the pending :down
+              for (;;) {
+                const double t_dn = next_event_time(0, n, true, t, ecur); ++n;
+                if (!end_time_resume(t, t_dn, rem, v)) break;
+                rem = v;
+                t = next_event_time(0, n, false, t_dn, ecur); ++n;
+              }
+              aj_ends = v;
+            }
+          }
           curjob = id; occ |= 1; STARTED(0) = id;
           setb(s_jt, (int)(id & Rm), (uint32_t)type);
           p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
@@ -385,13 +487,15 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
           hmix(h, (uint64_t)(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN) | ((uint64_t)i << 8));
           hmix(h, d2bits(clock)); hmix(h, 0);
         }
-        if (p.up_down) mark_seen(i);
+        if (p.up_down) { mark_seen(i); if (LOG) stage_msg(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN, i, 0, 0u); }
         fired |= bit;
         if (dup & bit) { dup &= ~bit; up ^= bit; }           // re-fire of an already realised event
         else {
           const double t_fire = FUT_T(i);
           const uint32_t n = FUT_N(i);
-          const double t_next = next_event_time(i, n, was_up_event, t_fire);
+          uint32_t ecur = REPLAY ? s_eidx[i * nt] : 0u;
+          const double t_next = next_event_time(i, n, was_up_event, t_fire, ecur);
+          if (REPLAY) s_eidx[i * nt] = ecur;
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
           if (was_up_event && (pend & bit)) {                // end-time resumes at this :up  core.clj:145-151
             double v;
@@ -409,6 +513,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
         const int n = (int)getb(s_cnt, i);
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ENDS(i))); }
         mark_seen(i);
+        if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
         if (has_bj & bit) status = MJP_INST_TICK_OVERFLOW;
         has_bj |= bit;
         rtbj |= bit & ~has_sm;
@@ -419,6 +524,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
         const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(ENDS(i))); }
         mark_seen(i);
+        if (LOG) stage_msg(MJP_ACT_EJ, i, 0, id);
         if (has_ej) status = MJP_INST_TICK_OVERFLOW;
         has_ej = true; ej_ent = ent;
       }
@@ -434,6 +540,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
       start_job(i, type);
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);
+      if (LOG) stage_msg(MJP_ACT_SM, i, n, id);
       if (has_sm & bbit) status = MJP_INST_TICK_OVERFLOW;
       has_sm |= bbit;
       setb(s_cnt, b, (uint32_t)(n - 1));
@@ -451,6 +558,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
         const MaskT bit = MJP_BIT(i);
         if (HASH) { hmix(h, (uint64_t)(MJP_ACT_ST + which) | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); }
         mark_seen(i);
+        if (LOG) stage_msg(MJP_ACT_ST + which, i, 0, 0u);
         if (which < 2) { S ^= bit; toggle(tgS_lo, tgS_hi, bit); }
         else { B ^= bit; toggle(tgB_lo, tgB_hi, bit); }
       }

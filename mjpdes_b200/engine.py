@@ -92,6 +92,10 @@ class Handle:
         self._check(self._lib.mjp_upload(self._h, C.byref(desc), int(n_inst)))
         self._line, self._n = line, int(n_inst)
 
+    def reserve_log(self, capacity: int):
+        """Device buffer for SCADA records; needed before ``launch(want_log=True)``."""
+        self._check(self._lib.mjp_reserve_log(self._h, int(capacity)))
+
     def launch(self, mode: int = abi.RNG_COUNTER, seed: int = 0, first_instance_id: int = 0, want_log: bool = False):
         rng = abi.RngSpec(mode, 0, seed, first_instance_id)
         self._check(self._lib.mjp_launch(self._h, C.byref(rng), int(want_log)))

@@ -6,7 +6,7 @@
 #include <vector>
 
 extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
-                           int want_hash) {
+                           int want_hash, mjp_log_out *log) {
   mjp::LinePlan pl = mjp::build_plan(L, n_inst);
   mjp::KParams kp = pl.kp;
   const int M = kp.M;
@@ -26,19 +26,27 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   kp.hash = s->event_hash; kp.status = s->status;
   if (pl.kp.const_bytes + pl.per_thread_bytes > sizeof(mjp::smem_raw)) return MJP_ERR_UNSUPPORTED;
   const bool replay = rng->mode == MJP_RNG_REPLAY, hash = want_hash != 0;
+  unsigned long long cursor[2] = {0, 0};
+  const bool want_log = log && L->log;
+  if (want_log) { kp.log_records = log->records; kp.log_capacity = log->capacity; kp.log_cursor = cursor; }
   gridDim.x = (unsigned)n_inst;
   for (uint64_t g = 0; g < n_inst; ++g) {
     blockIdx.x = (unsigned)g;
-#define RUN(MT) \
-    if (replay && hash && sweep) mjp::mjp_line_kernel<MT, true, true, true>(kp); \
-    else if (replay && hash) mjp::mjp_line_kernel<MT, true, true, false>(kp); \
-    else if (replay && sweep) mjp::mjp_line_kernel<MT, true, false, true>(kp); \
-    else if (replay) mjp::mjp_line_kernel<MT, true, false, false>(kp); \
-    else if (hash && sweep) mjp::mjp_line_kernel<MT, false, true, true>(kp); \
-    else if (hash) mjp::mjp_line_kernel<MT, false, true, false>(kp); \
-    else if (sweep) mjp::mjp_line_kernel<MT, false, false, true>(kp); \
-    else mjp::mjp_line_kernel<MT, false, false, false>(kp);
+#define RUN2(MT, LG) \
+    if (replay && hash && sweep) mjp::mjp_line_kernel<MT, true, true, true, LG>(kp); \
+    else if (replay && hash) mjp::mjp_line_kernel<MT, true, true, false, LG>(kp); \
+    else if (replay && sweep) mjp::mjp_line_kernel<MT, true, false, true, LG>(kp); \
+    else if (replay) mjp::mjp_line_kernel<MT, true, false, false, LG>(kp); \
+    else if (hash && sweep) mjp::mjp_line_kernel<MT, false, true, true, LG>(kp); \
+    else if (hash) mjp::mjp_line_kernel<MT, false, true, false, LG>(kp); \
+    else if (sweep) mjp::mjp_line_kernel<MT, false, false, true, LG>(kp); \
+    else mjp::mjp_line_kernel<MT, false, false, false, LG>(kp);
+#define RUN(MT) if (want_log) { RUN2(MT, true) } else { RUN2(MT, false) }
     if (M <= 32) { RUN(uint32_t) } else { RUN(uint64_t) }
+  }
+  if (log) {
+    log->count = cursor[0] < log->capacity ? cursor[0] : log->capacity;
+    log->dropped = cursor[1];
   }
   if (s->aggregate) {
     const int n_metrics = 3 * M + 1, len = 1 + 2 * n_metrics;
