@@ -144,6 +144,22 @@ def main():
         out[gid] = {"cite": f"log_test.clj {mname}/{tname}", "model": plain(model), "cycle": tuple6,
                     "span": span, "from_clk": start, "pulled": pulled, "tol": 1e-9}
 
+    # SCADA text lines quoted in the comments of log_test.clj:45-51,62-68 (print-lines output format)
+    import re
+    text = open(LOG_TEST).read()
+    quoted = re.findall(r"^;;; (\{:clk.*\})\s*$", text, flags=re.M)
+    out["G8"]["scada_text"] = quoted[:6]
+    out["G9"]["scada_text"] = quoted[6:12]
+
+    # the reference's own model files, parsed (resources/*.clj, data/*.clj): inputs, not expected values
+    out["models"] = {}
+    for rel in ("resources/example.clj", "resources/example2.clj", "data/example-10.clj", "data/submodel-1.clj",
+                "data/quick.clj"):
+        out["models"][rel] = plain(edn.read_file(os.path.join(REF, rel)))
+    # recorded outputs quoted by SURVEY.md 6 (loose statistical sanity only; :blocked excluded)
+    out["recorded"] = {"data/new-out.clj": plain(edn.read_file(os.path.join(REF, "data/new-out.clj"))),
+                       "data/ex1-out-out.clj": plain(edn.read_file(os.path.join(REF, "data/ex1-out-out.clj")))}
+
     path = os.path.join(HERE, "reference_goldens.json")
     with open(path, "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
