@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -118,27 +119,56 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   return MJP_OK;
 }
 
-template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
+template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
 static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int threads, size_t smem, cudaStream_t st) {
-  auto k = mjp::mjp_line_kernel<MaskT, REPLAY, HASH, SWEEP, LOG>;
+  auto k = mjp::mjp_line_kernel<MaskT, MT, REPLAY, HASH, SWEEP, LOG>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<blocks, threads, smem, st>>>(kp);
   return cudaGetLastError();
 }
 
-template <typename MaskT>
-static cudaError_t launch_mask(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
-                               int threads, size_t smem, cudaStream_t st) {
-  const int v = (log ? 8 : 0) | (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
-#define MJP_CASE(n) \
-  case n: return launch_variant<MaskT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, ((n) & 8) != 0>(kp, blocks, threads, smem, st);
+// MT > 0 (register-resident :ends, exactly MT machines) exists without SCADA capture only.
+template <typename MaskT, int MT>
+static cudaError_t launch_flags(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
+                                int threads, size_t smem, cudaStream_t st) {
+  const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
+#define MJP_CASE(n, LG) \
+  case n: return launch_variant<MaskT, MT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, LG>(kp, blocks, threads, smem, st);
+  if constexpr (MT == 0) {
+    if (log) {
+      switch (v) {
+        MJP_CASE(0, true) MJP_CASE(1, true) MJP_CASE(2, true) MJP_CASE(3, true)
+        MJP_CASE(4, true) MJP_CASE(5, true) MJP_CASE(6, true) default: MJP_CASE(7, true)
+      }
+    }
+  }
   switch (v) {
-    MJP_CASE(0) MJP_CASE(1) MJP_CASE(2) MJP_CASE(3) MJP_CASE(4) MJP_CASE(5) MJP_CASE(6) MJP_CASE(7)
-    MJP_CASE(8) MJP_CASE(9) MJP_CASE(10) MJP_CASE(11) MJP_CASE(12) MJP_CASE(13) MJP_CASE(14)
-    default: return launch_variant<MaskT, true, true, true, true>(kp, blocks, threads, smem, st);
+    MJP_CASE(0, false) MJP_CASE(1, false) MJP_CASE(2, false) MJP_CASE(3, false)
+    MJP_CASE(4, false) MJP_CASE(5, false) MJP_CASE(6, false) default: MJP_CASE(7, false)
   }
 #undef MJP_CASE
+}
+
+static cudaError_t launch_line_kernel(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
+                                      int threads, size_t smem, cudaStream_t st) {
+#define MJP_ARGS replay, hash, sweep, log, kp, blocks, threads, smem, st
+  if (kp.M > 32) return launch_flags<uint64_t, 0>(MJP_ARGS);
+  static const bool force_generic = std::getenv("MJP_FORCE_GENERIC") != nullptr;   // A/B measurements only
+  if (!log && !force_generic) {
+    switch (kp.M) {
+      case 2: return launch_flags<uint32_t, 2>(MJP_ARGS);
+      case 3: return launch_flags<uint32_t, 3>(MJP_ARGS);
+      case 4: return launch_flags<uint32_t, 4>(MJP_ARGS);
+      case 5: return launch_flags<uint32_t, 5>(MJP_ARGS);
+      case 6: return launch_flags<uint32_t, 6>(MJP_ARGS);
+      case 7: return launch_flags<uint32_t, 7>(MJP_ARGS);
+      case 8: return launch_flags<uint32_t, 8>(MJP_ARGS);
+      default: break;
+    }
+  }
+  return launch_flags<uint32_t, 0>(MJP_ARGS);
+#undef MJP_ARGS
 }
 
 extern "C" {
@@ -316,9 +346,7 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
   {
     const int threads = h->block_threads;
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
-    cudaError_t e = (kp.M <= 32)
-        ? launch_mask<uint32_t>(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream)
-        : launch_mask<uint64_t>(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream);
+    cudaError_t e = launch_line_kernel(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream);
     CK(e);
     launches++;
   }

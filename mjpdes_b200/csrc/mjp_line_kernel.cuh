@@ -70,8 +70,10 @@ __device__ __forceinline__ bool end_time_resume(double t_up, double t_down, doub
 
 #define MJP_BIT(i) ((MaskT)1 << (i))
 
-template <typename MaskT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
-__global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kernel(const KParams p) {
+// MT > 0: the line has exactly MT machines and their :ends live in registers (fully unrolled scan);
+// MT == 0: any M, :ends in shared memory.
+template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
+__global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x, M = p.M, K = p.K;
@@ -98,15 +100,14 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
   double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
   uint32_t *su = reinterpret_cast<uint32_t *>(smem_raw + p.const_bytes + (size_t)p.nf64 * nt * 8) + tid;
 #define FUT_T(i)   sf[(i) * nt]                 /* :future etime                      */
-#define ENDS(i)    sf[(M + (i)) * nt]           /* :status :ends, or remaining work   */
+#define ENDS_S(i)  sf[(M + (i)) * nt]           /* :status :ends, or remaining work (MT == 0) */
 #define BS(i)      sf[(2 * M + (i)) * nt]       /* :bs (NaN = nil), util/log.clj:176  */
 #define SS(i)      sf[(3 * M + (i)) * nt]       /* :ss                                */
 #define LASTCLK(b) sf[(4 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
 #define FUT_N(i)   su[(i) * nt]                 /* :future index                      */
 #define STARTED(i) su[(M + (i)) * nt]           /* jobs started on machine i          */
-  uint32_t *s_cnt = su + (size_t)2 * M * nt;                      /* (count :holding), 4 per word */
-  const int cntw = (M - 1 + 3) >> 2;
-  uint32_t *s_jt = s_cnt + (size_t)cntw * nt;                     /* job type ring, 4 per word    */
+#define CNT(b)     su[(2 * M + (b)) * nt]       /* (count :holding) of buffer b       */
+  uint32_t *s_jt = su + (size_t)(3 * M - 1) * nt;                 /* job type ring, 4 per word    */
   uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * nt;              /* REPLAY: exponential cursor   */
   const uint32_t Rm = (uint32_t)p.R - 1;
 
@@ -129,6 +130,23 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
       return __ddiv_rn(wv, Wv);
     }
     return c_dur[k * M + i];
+  };
+
+  double r_end[MT > 0 ? MT : 1];
+  auto get_end = [&](int i) -> double {
+    if (MT > 0) {
+      double v = r_end[0];
+#pragma unroll
+      for (int j = 1; j < MT; ++j) v = (j == i) ? r_end[j] : v;
+      return v;
+    }
+    return ENDS_S(i);
+  };
+  auto set_end = [&](int i, double v) {
+    if (MT > 0) {
+#pragma unroll
+      for (int j = 0; j < MT; ++j) if (j == i) r_end[j] = v;
+    } else ENDS_S(i) = v;
   };
 
   const uint64_t gid = p.first_id + g;
@@ -181,13 +199,25 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
     FUT_T(i) = __ddiv_rn(-det_log(eu), is_up ? lam : mu);
     FUT_N(i) = 0u;
     STARTED(i) = 0u;
-    ENDS(i) = 0.0;
+    set_end(i, 0.0);
     BS(i) = QNAN;
     SS(i) = QNAN;
     if (is_up) up |= MJP_BIT(i);
   }
   for (int b = 0; active && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
-  for (int q = 0; active && q < cntw; ++q) s_cnt[q * nt] = 0u;
+  for (int b = 0; active && b < M - 1; ++b) CNT(b) = 0u;
+  // min over the machines' pending up/down times and who attains it: changes only when one fires
+  double tmin_ud = INF;
+  MaskT m_udc = 0;
+  auto rescan_fut = [&]() {
+    tmin_ud = INF; m_udc = 0;
+    for (int i = 0; i < M; ++i) {
+      const double t = FUT_T(i);
+      if (t < tmin_ud) { tmin_ud = t; m_udc = 0; }
+      if (t == tmin_ud) m_udc |= MJP_BIT(i);
+    }
+  };
+  if (active) rescan_fut();
 
   // ---- model state in registers ---------------------------------------------
   double clock = 0.0;
@@ -331,7 +361,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
     // elapsed time, the others add (clk - clk) = 0.
     for (MaskT q = warm ? (has_bj | has_sm) : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
       const int b = MO::ffs(q); q &= q - 1;
-      const int cf = (int)getb(s_cnt, b);
+      const int cf = (int)CNT(b);
       const bool bj = (has_bj >> b) & 1, sm = (has_sm >> b) & 1, bj_first_rt = (rtbj >> b) & 1;
       // levels seen by the :bj and the :sm of this tick, from the final count cf
       const int n_bj = sm ? (bj_first_rt ? cf : cf - 1) : cf - 1;
@@ -354,7 +384,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
     const MaskT bit = MJP_BIT(i);
     double v;
     if (end_time_begin((up & bit) != 0, FUT_T(i), clock, dur_of(type, i), v)) pend |= bit; else pend &= ~bit;
-    ENDS(i) = v;
+    set_end(i, v);
   };
 
   // ======================= main-loop-loop, core.clj:729-744 =======================
@@ -384,14 +414,14 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
     const MaskT st_chk = ~S & empty & occ & ~pend;             // finished? needs clock >= :ends, utils.clj:68-74
 
     // One fixed-trip pass over the machines (every lane does the same work): min over the timed
-    // candidates, remembering who attains it, and the finished? bits new-starved? needs.
-    double tmin = INF;
-    MaskT m_ud = 0, m_tb = 0, m_bl = 0, fin = ~occ;
-    for (int i = 0; i < M; ++i) {
+    // candidates, remembering who attains it, and the finished? bits new-starved? needs.  The up/down
+    // candidates (core.clj:356-372) enter through the cached (tmin_ud, m_udc).
+    double tmin = tmin_ud;
+    MaskT m_ud = m_udc, m_tb = 0, m_bl = 0, fin = ~occ;
+#pragma unroll
+    for (int i = 0; i < (MT > 0 ? MT : M); ++i) {
       const MaskT bit = MJP_BIT(i);
-      const double tf = FUT_T(i), en = ENDS(i);
-      if (tf < tmin) { tmin = tf; m_ud = m_tb = m_bl = 0; }                                   // core.clj:356-372
-      if (tf == tmin) m_ud |= bit;
+      const double en = MT > 0 ? r_end[i] : ENDS_S(i);
       const bool is_tb = (c_tb & bit) != 0, is_bl = (c_bla & bit) != 0;
       const double tj = is_tb ? fmax(clock, en) : (is_bl ? en : INF);
       if (tj < tmin) { tmin = tj; m_ud = m_tb = m_bl = 0; }
@@ -455,9 +485,9 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
             stage_msg(MJP_ACT_AJ, 0, type, id);
             // the :aj record carries :ends (core.clj:250): when the lazy end-time is still pending, run the
             // literal look-ahead of core.clj:141-151 over events that are generated but not committed
-            if (!(pend & 1)) aj_ends = ENDS(0);
+            if (!(pend & 1)) aj_ends = get_end(0);
             else {
-              double rem = ENDS(0), t = FUT_T(0), v;
+              double rem = get_end(0), t = FUT_T(0), v;
               uint32_t n = FUT_N(0), ecur = REPLAY ? s_eidx[0] : 0u;
               if (up & 1) { t = next_event_time(0, n, false, t, ecur); ++n; }      // the :up after the pending :down
               for (;;) {
@@ -499,9 +529,10 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
           if (was_up_event && (pend & bit)) {                // end-time resumes at this :up  core.clj:145-151
             double v;
-            if (!end_time_resume(t_fire, t_next, ENDS(i), v)) pend &= ~bit;
-            ENDS(i) = v;
+            if (!end_time_resume(t_fire, t_next, get_end(i), v)) pend &= ~bit;
+            set_end(i, v);
           }
+          rescan_fut();
         }
       }
     }
@@ -510,19 +541,19 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
       const MaskT bit = MJP_BIT(i);
       const uint32_t id = STARTED(i);
       if (i < M - 1) {
-        const int n = (int)getb(s_cnt, i);
-        if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ENDS(i))); }
+        const int n = (int)CNT(i);
+        if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
         if (has_bj & bit) status = MJP_INST_TICK_OVERFLOW;
         has_bj |= bit;
         rtbj |= bit & ~has_sm;
-        setb(s_cnt, i, (uint32_t)(n + 1));
+        CNT(i) = (uint32_t)(n + 1);
         if (n + 1 == cap_of(i)) full |= bit;
         empty &= ~(bit << 1);
       } else {
         const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
-        if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(ENDS(i))); }
+        if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_EJ, i, 0, id);
         if (has_ej) status = MJP_INST_TICK_OVERFLOW;
@@ -534,7 +565,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
       const int i = MO::ffs(q); q &= q - 1;
       const MaskT bit = MJP_BIT(i), bbit = bit >> 1;
       const int b = i - 1;
-      const int n = (int)getb(s_cnt, b);
+      const int n = (int)CNT(b);
       const uint32_t id = STARTED(i) + 1;
       const int type = (int)getb(s_jt, (int)(id & Rm));
       start_job(i, type);
@@ -543,7 +574,7 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
       if (LOG) stage_msg(MJP_ACT_SM, i, n, id);
       if (has_sm & bbit) status = MJP_INST_TICK_OVERFLOW;
       has_sm |= bbit;
-      setb(s_cnt, b, (uint32_t)(n - 1));
+      CNT(b) = (uint32_t)(n - 1);
       if (n - 1 == 0) empty |= bit;
       full &= ~bbit;
       occ |= bit; STARTED(i) = id;
@@ -579,7 +610,8 @@ __global__ void __launch_bounds__(128, sizeof(MaskT) == 4 ? 6 : 3) mjp_line_kern
   if (HASH && p.hash) p.hash[g] = h;
   p.status[g] = (uint8_t)status;
 #undef FUT_T
-#undef ENDS
+#undef ENDS_S
+#undef CNT
 #undef BS
 #undef SS
 #undef LASTCLK

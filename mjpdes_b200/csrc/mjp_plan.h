@@ -67,7 +67,7 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   // cleaned order (1 B each).  A tick holds at most a handful of messages per machine.
   kp.stage_cap = L->log ? 3 * M + 8 : 0;
   kp.nf64 = 5 * M - 1 + kp.stage_cap;
-  kp.nu32 = 2 * M + ((M - 1 + 3) >> 2) + (R >> 2) + M      // the last M: REPLAY exponential cursors
+  kp.nu32 = 2 * M + (M - 1) + (R >> 2) + M                 // the last M: REPLAY exponential cursors
             + ((kp.stage_cap + 3) >> 2);
   kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
   pl.per_thread_bytes = (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;

@@ -32,17 +32,28 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   gridDim.x = (unsigned)n_inst;
   for (uint64_t g = 0; g < n_inst; ++g) {
     blockIdx.x = (unsigned)g;
-#define RUN2(MT, LG) \
-    if (replay && hash && sweep) mjp::mjp_line_kernel<MT, true, true, true, LG>(kp); \
-    else if (replay && hash) mjp::mjp_line_kernel<MT, true, true, false, LG>(kp); \
-    else if (replay && sweep) mjp::mjp_line_kernel<MT, true, false, true, LG>(kp); \
-    else if (replay) mjp::mjp_line_kernel<MT, true, false, false, LG>(kp); \
-    else if (hash && sweep) mjp::mjp_line_kernel<MT, false, true, true, LG>(kp); \
-    else if (hash) mjp::mjp_line_kernel<MT, false, true, false, LG>(kp); \
-    else if (sweep) mjp::mjp_line_kernel<MT, false, false, true, LG>(kp); \
-    else mjp::mjp_line_kernel<MT, false, false, false, LG>(kp);
-#define RUN(MT) if (want_log) { RUN2(MT, true) } else { RUN2(MT, false) }
-    if (M <= 32) { RUN(uint32_t) } else { RUN(uint64_t) }
+#define RUN3(MK, MT, LG) \
+    if (replay && hash && sweep) mjp::mjp_line_kernel<MK, MT, true, true, true, LG>(kp); \
+    else if (replay && hash) mjp::mjp_line_kernel<MK, MT, true, true, false, LG>(kp); \
+    else if (replay && sweep) mjp::mjp_line_kernel<MK, MT, true, false, true, LG>(kp); \
+    else if (replay) mjp::mjp_line_kernel<MK, MT, true, false, false, LG>(kp); \
+    else if (hash && sweep) mjp::mjp_line_kernel<MK, MT, false, true, true, LG>(kp); \
+    else if (hash) mjp::mjp_line_kernel<MK, MT, false, true, false, LG>(kp); \
+    else if (sweep) mjp::mjp_line_kernel<MK, MT, false, false, true, LG>(kp); \
+    else mjp::mjp_line_kernel<MK, MT, false, false, false, LG>(kp);
+    // the same dispatch as launch_line_kernel in mjp_abi.cu
+    if (M > 32) { if (want_log) { RUN3(uint64_t, 0, true) } else { RUN3(uint64_t, 0, false) } }
+    else if (want_log) { RUN3(uint32_t, 0, true) }
+    else switch (M) {
+      case 2: RUN3(uint32_t, 2, false) break;
+      case 3: RUN3(uint32_t, 3, false) break;
+      case 4: RUN3(uint32_t, 4, false) break;
+      case 5: RUN3(uint32_t, 5, false) break;
+      case 6: RUN3(uint32_t, 6, false) break;
+      case 7: RUN3(uint32_t, 7, false) break;
+      case 8: RUN3(uint32_t, 8, false) break;
+      default: RUN3(uint32_t, 0, false) break;
+    }
   }
   if (log) {
     log->count = cursor[0] < log->capacity ? cursor[0] : log->capacity;
