@@ -82,7 +82,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   if (!L) return fail(h, MJP_ERR_INVALID, "line descriptor is NULL");
   if (n_inst == 0) return fail(h, MJP_ERR_INVALID, "n_inst must be >= 1");
-  if (n_inst > (1ull << 32)) return fail(h, MJP_ERR_UNSUPPORTED, "more than 2^32 instances per call");
+  if (n_inst >= (1ull << 31)) return fail(h, MJP_ERR_UNSUPPORTED, "2^31 or more instances per call");
   if (L->M < 2) return fail(h, MJP_ERR_INVALID, ":line needs at least two machines and a buffer (core.clj:120)");
   if (L->M > MJP_MAX_MACHINES) return fail(h, MJP_ERR_UNSUPPORTED, "more than 64 machines");
   if (L->K < 1) return fail(h, MJP_ERR_INVALID, ":jobmix is empty (core.clj:117)");
@@ -155,7 +155,7 @@ static cudaError_t launch_line_kernel(bool replay, bool hash, bool sweep, bool l
 #define MJP_ARGS replay, hash, sweep, log, kp, blocks, threads, smem, st
   if (kp.M > 32) return launch_flags<uint64_t, 0>(MJP_ARGS);
   static const bool force_generic = std::getenv("MJP_FORCE_GENERIC") != nullptr;   // A/B measurements only
-  if (!log && !force_generic) {
+  if (!log && !force_generic && threads == MJP_FIXED_NT) {
     switch (kp.M) {
       case 2: return launch_flags<uint32_t, 2>(MJP_ARGS);
       case 3: return launch_flags<uint32_t, 3>(MJP_ARGS);
@@ -277,8 +277,9 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   size_t off = 0;
   auto plane = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   h->o_blk = plane(n * M * 8); h->o_stv = plane(n * M * 8); h->o_occ = plane(n * (size_t)levels * 8);
+  h->o_njobs = plane(n * 8); h->o_res = plane(n * 8);
   h->zero_bytes = off;
-  h->o_njobs = plane(n * 8); h->o_res = plane(n * 8); h->o_clk = plane(n * 8); h->o_cur = plane(n * 8);
+  h->o_clk = plane(n * 8); h->o_cur = plane(n * 8);
   h->o_nev = plane(n * 8); h->o_hash = plane(n * 8); h->o_status = plane(n);
   h->out_bytes = off;
   CK(h->d_out.reserve(off));

@@ -68,7 +68,45 @@ __device__ __forceinline__ bool end_time_resume(double t_up, double t_down, doub
   v = rem - avail; return true;
 }
 
+// The heavy arithmetic (Philox + ln, ~180 instructions) is needed by ~5 % of the events.  It is kept
+// out of line so that its temporaries do not raise the register pressure of the whole micro-step loop
+// (inlined, the loop spilled its bitmasks to local memory).
+#ifndef MJP_NOINLINE
+#define MJP_NOINLINE __noinline__
+#endif
+// sojourn of COUNTER mode: Erlang-2 from one Philox block {idx, consumer, gid}
+__device__ MJP_NOINLINE double sojourn_counter(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate) {
+  uint32_t o[4];
+  philox4x32_10(idx, consumer, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  return __ddiv_rn(-det_log(__dmul_rn(u52open(o[0], o[1]), u52open(o[2], o[3]))), rate);
+}
+// sojourn of REPLAY mode: the literal loop of core.clj:185-191; e is the cursor of the exponential stream
+__device__ MJP_NOINLINE double sojourn_replay(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate,
+                                             uint32_t *e_io) {
+  uint32_t o[4], e = *e_io;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), g0 = (uint32_t)gid, g1 = (uint32_t)(gid >> 32);
+  philox4x32_10(idx, consumer, g0, g1, k0, k1, o);
+  const double some_num = u53(o[0], o[1]);                                     // core.clj:185
+  philox4x32_10(e++, consumer + 1u, g0, g1, k0, k1, o);
+  double T = __ddiv_rn(-det_log(u52open(o[0], o[1])), rate);                   // core.clj:187
+  while (!(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {        // core.clj:188, 162-165
+    philox4x32_10(e++, consumer + 1u, g0, g1, k0, k1, o);
+    T = __dadd_rn(T, __ddiv_rn(-det_log(u52open(o[0], o[1])), rate));          // core.clj:190-191
+  }
+  *e_io = e;
+  return T;
+}
+// the two uniforms of job-type block `blk` (consumer 0)
+__device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid, uint64_t seed, double *u0, double *u1) {
+  uint32_t o[4];
+  philox4x32_10(blk, 0u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  *u0 = u53(o[0], o[1]); *u1 = u53(o[2], o[3]);
+}
+
 #define MJP_BIT(i) ((MaskT)1 << (i))
+#ifndef MJP_FIXED_NT
+#define MJP_FIXED_NT 64      /* CTA size of the MT > 0 variants (compile-time [slot][thread] strides) */
+#endif
 
 // MT > 0: the line has exactly MT machines and their :ends live in registers (fully unrolled scan);
 // MT == 0: any M, :ends in shared memory.
@@ -76,7 +114,7 @@ template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
 __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, nt = blockDim.x, M = p.M, K = p.K;
+  const int tid = threadIdx.x, nt = (MT > 0) ? MJP_FIXED_NT : (int)blockDim.x, M = (MT > 0) ? MT : p.M, K = p.K;
 
   // ---- CTA constant table --------------------------------------------------
   double *c_lam = reinterpret_cast<double *>(smem_raw);
@@ -91,8 +129,8 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   for (int q = tid; q < M - 1; q += nt) { c_N[q] = p.N[q]; c_lvl[q] = p.lvl[q]; }
   __syncthreads();
 
-  const uint64_t g = (uint64_t)blockIdx.x * nt + tid;
-  const uint64_t n_inst = p.n_inst;
+  const uint32_t g = blockIdx.x * (uint32_t)nt + tid;        // instances per call < 2^31 (mjp_upload)
+  const uint32_t n_inst = (uint32_t)p.n_inst;
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
   bool active = g < n_inst;
 
@@ -149,9 +187,11 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
     } else ENDS_S(i) = v;
   };
 
-  const uint64_t gid = p.first_id + g;
-  const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
-  const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+  // Philox block {idx, consumer, instance id} under key = seed; nothing of it is kept live in registers
+  auto px = [&](uint32_t idx, uint32_t consumer, uint32_t o[4]) {
+    const uint64_t gid = p.first_id + g;
+    philox4x32_10(idx, consumer, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32), o);
+  };
   const MaskT ALL = (M >= (int)(8 * sizeof(MaskT))) ? ~(MaskT)0 : (MJP_BIT(M) - 1);
   const MaskT bbs = (MaskT)p.bbs_mask;
   const double INF = __longlong_as_double(0x7FF0000000000000ll);
@@ -161,21 +201,9 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   // `e` is the machine's cursor in its exponential stream (REPLAY only); the caller decides whether to commit it.
   auto next_event_time = [&](int i, uint32_t n_prev, bool prev_is_up, double t_prev, uint32_t &e) -> double {
     const double rate = prev_is_up ? lam_of(i) : mu_of(i);
-    uint32_t o[4];
-    double T;
-    if (REPLAY) {
-      philox4x32_10(n_prev + 1, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
-      const double some_num = u53(o[0], o[1]);                                   // core.clj:185
-      philox4x32_10(e++, 2u + 2u * i, g_lo, g_hi, k0, k1, o);
-      T = __ddiv_rn(-det_log(u52open(o[0], o[1])), rate);                        // core.clj:187
-      while (!(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {      // core.clj:188, 162-165
-        philox4x32_10(e++, 2u + 2u * i, g_lo, g_hi, k0, k1, o);
-        T = __dadd_rn(T, __ddiv_rn(-det_log(u52open(o[0], o[1])), rate));        // core.clj:190-191
-      }
-    } else {
-      philox4x32_10(n_prev + 1, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
-      T = __ddiv_rn(-det_log(__dmul_rn(u52open(o[0], o[1]), u52open(o[2], o[3]))), rate);   // Erlang-2
-    }
+    const uint64_t gid = p.first_id + g;
+    const double T = REPLAY ? sojourn_replay(n_prev + 1, 1u + 2u * i, gid, p.seed, rate, &e)
+                            : sojourn_counter(n_prev + 1, 1u + 2u * i, gid, p.seed, rate);
     return __dadd_rn(t_prev, T);
   };
 
@@ -185,12 +213,12 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
     const double lam = lam_of(i), mu = mu_of(i);
     const double p_up = __ddiv_rn(mu, __dadd_rn(lam, mu));
     uint32_t o[4];
-    philox4x32_10(0u, 1u + 2u * i, g_lo, g_hi, k0, k1, o);
+    px(0u, 1u + 2u * i, o);
     const bool is_up = u53(o[0], o[1]) < p_up;
     double eu;
     if (REPLAY) {
       uint32_t o2[4];
-      philox4x32_10(0u, 2u + 2u * i, g_lo, g_hi, k0, k1, o2);
+      px(0u, 2u + 2u * i, o2);
       eu = u52open(o2[0], o2[1]);
       s_eidx[i * nt] = 1u;
     } else {
@@ -225,7 +253,9 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   MaskT empty = ALL & ~(MaskT)1;               // feed-buffer-empty? (nil for the entry machine, utils.clj:85)
   const MaskT upj = p.jm2dm ? ALL : (MaskT)0;  // :jm2dm, core.clj:490,495
   uint32_t curjob = 0;
-  uint64_t n_events = 0, iters = 0;
+  uint64_t n_events = 0;
+  uint32_t iters = 0;
+  const uint32_t iter_cap = p.max_iter > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)p.max_iter;
   uint64_t h = 0xcbf29ce484222325ull;
   // tick state (what :log-buf holds, util/log.clj:89-109)
   double tick_clk = 0.0, ej_ent = 0.0;
@@ -233,8 +263,6 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   MaskT tgB_lo = 0, tgB_hi = 0, tgS_lo = 0, tgS_hi = 0, B0 = 0, S0 = 0;
   bool has_ej = false;
   // steady accumulators kept in registers
-  double residence = 0.0;
-  long long njobs = 0;
   int status = MJP_INST_NOT_RUN;
 
   int type_cache = -2;                 // job type of the NEXT job when already drawn (-2: not drawn)
@@ -372,7 +400,10 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
       red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
       LASTCLK(b) = tick_clk;
     }
-    if (warm && has_ej) { residence = residence + (tick_clk - ej_ent); njobs++; }   // end-job util/log.clj:212-217
+    if (warm && has_ej) {                                                    // end-job util/log.clj:212-217
+      red_add(p.residence + g, tick_clk - ej_ent);
+      atomicAdd(reinterpret_cast<unsigned long long *>(p.njobs) + g, 1ull);
+    }
     if (LOG) emit_tick(fm);
     seen = lead = has_bj = has_sm = rtbj = 0;
     tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
@@ -400,7 +431,7 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
     // end-main-loop? core.clj:722-727
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
       status = MJP_INST_NORMAL_END; live = false;
-    } else if (++iters > p.max_iter) { status = MJP_INST_ITER_LIMIT; live = false; }
+    } else if (++iters == iter_cap) { status = MJP_INST_ITER_LIMIT; live = false; }
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -468,10 +499,10 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
         if (K == 1 && c_thr[0] >= 1.0) type = 0;
         else if (type_cache != -2) { type = type_cache; type_cache = -2; }
         else {
-          uint32_t o[4];
-          philox4x32_10(curjob >> 1, 0u, g_lo, g_hi, k0, k1, o);
-          if (curjob & 1) type = type_from(u53(o[2], o[3]));
-          else { type = type_from(u53(o[0], o[1])); type_cache = type_from(u53(o[2], o[3])); }
+          double u0, u1;
+          jobtype_uniforms(curjob >> 1, p.first_id + g, p.seed, &u0, &u1);
+          if (curjob & 1) type = type_from(u1);
+          else { type = type_from(u0); type_cache = type_from(u1); }
         }
         if (type < 0) {                                      // the reference dies in job-requires
           status = MJP_INST_JOBTYPE_NIL; live = false;
@@ -602,8 +633,6 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   if (g >= n_inst) return;
 
   // the reference never flushes the last tick: whatever is still in :log-buf is lost
-  if (p.njobs) p.njobs[g] = njobs;
-  if (p.residence) p.residence[g] = residence;
   if (p.final_clock) p.final_clock[g] = clock;
   if (p.curjob) p.curjob[g] = (long long)curjob;
   if (p.n_events) p.n_events[g] = n_events;

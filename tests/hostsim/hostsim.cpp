@@ -1,5 +1,6 @@
 // hostsim.cpp -- TEST-ONLY host execution of the kernel source (see cuda_shim.h).
 #include "cuda_shim.h"
+#define MJP_FIXED_NT 1        /* the shim runs one thread per block */
 #include "../../mjpdes_b200/csrc/mjp_line_kernel.cuh"
 #include "../../mjpdes_b200/csrc/mjp_plan.h"
 
@@ -21,6 +22,7 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   kp.enters = enters.data();
   for (size_t q = 0; q < (size_t)M * n_inst; ++q) { s->blocked_time[q] = 0; s->starved_time[q] = 0; }
   for (size_t q = 0; q < (size_t)kp.L * n_inst; ++q) s->occ_time[q] = 0;
+  for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; }
   kp.njobs = s->njobs; kp.residence = s->residence_sum; kp.blocked = s->blocked_time; kp.starved = s->starved_time;
   kp.occ = s->occ_time; kp.final_clock = s->final_clock; kp.curjob = s->current_job; kp.n_events = s->n_events;
   kp.hash = s->event_hash; kp.status = s->status;
