@@ -150,12 +150,16 @@ static cudaError_t launch_flags(bool replay, bool hash, bool sweep, bool log, co
 #undef MJP_CASE
 }
 
+static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
+  static const bool force_generic = std::getenv("MJP_FORCE_GENERIC") != nullptr;   // A/B measurements only
+  return !log && !force_generic && threads == MJP_FIXED_NT && kp.M >= 2 && kp.M <= 8;
+}
+
 static cudaError_t launch_line_kernel(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
                                       int threads, size_t smem, cudaStream_t st) {
 #define MJP_ARGS replay, hash, sweep, log, kp, blocks, threads, smem, st
   if (kp.M > 32) return launch_flags<uint64_t, 0>(MJP_ARGS);
-  static const bool force_generic = std::getenv("MJP_FORCE_GENERIC") != nullptr;   // A/B measurements only
-  if (!log && !force_generic && threads == MJP_FIXED_NT) {
+  if (use_register_ends(kp, log, threads)) {
     switch (kp.M) {
       case 2: return launch_flags<uint32_t, 2>(MJP_ARGS);
       case 3: return launch_flags<uint32_t, 3>(MJP_ARGS);
@@ -277,10 +281,10 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   size_t off = 0;
   auto plane = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   h->o_blk = plane(n * M * 8); h->o_stv = plane(n * M * 8); h->o_occ = plane(n * (size_t)levels * 8);
-  h->o_njobs = plane(n * 8); h->o_res = plane(n * 8);
+  h->o_njobs = plane(n * 8); h->o_res = plane(n * 8); h->o_nev = plane(n * 8);
   h->zero_bytes = off;
   h->o_clk = plane(n * 8); h->o_cur = plane(n * 8);
-  h->o_nev = plane(n * 8); h->o_hash = plane(n * 8); h->o_status = plane(n);
+  h->o_hash = plane(n * 8); h->o_status = plane(n);
   h->out_bytes = off;
   CK(h->d_out.reserve(off));
   char *ob = (char *)h->d_out.ptr;
@@ -346,6 +350,8 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
   if (h->want_log && !kp.log_records) return fail(h, MJP_ERR_INVALID, "SCADA capture wanted: call mjp_reserve_log first");
   {
     const int threads = h->block_threads;
+    const bool mt = use_register_ends(kp, h->want_log, threads);
+    h->smem_bytes = (size_t)kp.const_bytes + mjp::plan_layout(kp, mt, replay, h->want_log) * threads;
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
     cudaError_t e = launch_line_kernel(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream);
     CK(e);

@@ -111,7 +111,7 @@ __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid, uint64
 // MT > 0: the line has exactly MT machines and their :ends live in registers (fully unrolled scan);
 // MT == 0: any M, :ends in shared memory.
 template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
-__global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168) mjp_line_kernel(const KParams p) {
+__global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = (MT > 0) ? MJP_FIXED_NT : (int)blockDim.x, M = (MT > 0) ? MT : p.M, K = p.K;
@@ -138,15 +138,17 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
   uint32_t *su = reinterpret_cast<uint32_t *>(smem_raw + p.const_bytes + (size_t)p.nf64 * nt * 8) + tid;
 #define FUT_T(i)   sf[(i) * nt]                 /* :future etime                      */
-#define ENDS_S(i)  sf[(M + (i)) * nt]           /* :status :ends, or remaining work (MT == 0) */
-#define BS(i)      sf[(2 * M + (i)) * nt]       /* :bs (NaN = nil), util/log.clj:176  */
-#define SS(i)      sf[(3 * M + (i)) * nt]       /* :ss                                */
-#define LASTCLK(b) sf[(4 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
+#define BS(i)      sf[(M + (i)) * nt]           /* :bs (NaN = nil), util/log.clj:176  */
+#define SS(i)      sf[(2 * M + (i)) * nt]       /* :ss                                */
+#define LASTCLK(b) sf[(3 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
+#define TICKCLK    sf[(4 * M - 1) * nt]         /* :clk of the messages in :log-buf   */
+#define EJENT      sf[(4 * M) * nt]             /* :ent of this tick's :ej            */
+#define ENDS_S(i)  sf[(4 * M + 1 + (i)) * nt]   /* :status :ends, or remaining work (MT == 0 only) */
 #define FUT_N(i)   su[(i) * nt]                 /* :future index                      */
 #define STARTED(i) su[(M + (i)) * nt]           /* jobs started on machine i          */
 #define CNT(b)     su[(2 * M + (b)) * nt]       /* (count :holding) of buffer b       */
   uint32_t *s_jt = su + (size_t)(3 * M - 1) * nt;                 /* job type ring, 4 per word    */
-  uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * nt;              /* REPLAY: exponential cursor   */
+  uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * nt;              /* REPLAY only: exponential cursor */
   const uint32_t Rm = (uint32_t)p.R - 1;
 
   auto getb = [&](uint32_t *base, int idx) -> uint32_t {
@@ -253,12 +255,12 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   MaskT empty = ALL & ~(MaskT)1;               // feed-buffer-empty? (nil for the entry machine, utils.clj:85)
   const MaskT upj = p.jm2dm ? ALL : (MaskT)0;  // :jm2dm, core.clj:490,495
   uint32_t curjob = 0;
-  uint64_t n_events = 0;
+  uint32_t n_ev = 0;                            // run-action calls not yet added to p.n_events
   uint32_t iters = 0;
   const uint32_t iter_cap = p.max_iter > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)p.max_iter;
   uint64_t h = 0xcbf29ce484222325ull;
   // tick state (what :log-buf holds, util/log.clj:89-109)
-  double tick_clk = 0.0, ej_ent = 0.0;
+  bool tick_here = false;                       // TICKCLK == clock
   MaskT seen = 0, lead = 0, has_bj = 0, has_sm = 0, rtbj = 0;
   MaskT tgB_lo = 0, tgB_hi = 0, tgS_lo = 0, tgS_hi = 0, B0 = 0, S0 = 0;
   bool has_ej = false;
@@ -286,8 +288,9 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   };
   // ---- SCADA capture (LOG): :log-buf of the current tick, staged in shared memory ----
   // word: act | m << 8 | n << 16 | done << 31 | job << 32
-  unsigned long long *s_stage = reinterpret_cast<unsigned long long *>(sf + (size_t)(5 * M - 1) * nt);
-  uint32_t *s_ord = s_eidx + (size_t)M * nt;               // cleaned order, 4 indices per word
+  unsigned long long *s_stage =
+      reinterpret_cast<unsigned long long *>(sf + (size_t)(4 * M + 1 + (MT > 0 ? 0 : M)) * nt);
+  uint32_t *s_ord = s_eidx + (size_t)(REPLAY ? M : 0) * nt;   // cleaned order, 4 indices per word
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
   uint32_t line_cnt = 0;                                   // [:report :line-cnt]
@@ -301,8 +304,9 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   };
   // clean-log-buf (util/log.clj:38-57) + print-lines (util/log.clj:111-137): order the staged messages,
   // reserve space with ONE atomicAdd per warp, write 32-byte records.
-  auto emit_tick = [&](const unsigned fm) {
+  auto emit_tick = [&](const unsigned fm, const double tick_clk) {
     const int lane = tid & 31;
+    const double ej_ent = EJENT;
     const int ns = n_staged < stage_cap ? n_staged : stage_cap;
     const bool print_now = p.log_on && tick_clk >= p.warm_up && p.max_lines > (uint64_t)line_cnt;   // util/log.clj:220-226
     int k = 0;
@@ -371,6 +375,7 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   // push-log for the tick that just ended (util/log.clj:98-108): clean-log-buf + add-compute-log!.
   // Entered by the lanes of `fm`; its three loops are voted over `fm` so the lanes stay together.
   auto flush_tick = [&](const unsigned fm) {
+    const double tick_clk = TICKCLK;
     const bool warm = tick_clk >= p.warm_up;                               // util/log.clj:104
     // :bl/:ub of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed in order
     for (MaskT q = warm ? tgB_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
@@ -401,10 +406,11 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
       LASTCLK(b) = tick_clk;
     }
     if (warm && has_ej) {                                                    // end-job util/log.clj:212-217
-      red_add(p.residence + g, tick_clk - ej_ent);
+      red_add(p.residence + g, tick_clk - EJENT);
       atomicAdd(reinterpret_cast<unsigned long long *>(p.njobs) + g, 1ull);
     }
-    if (LOG) emit_tick(fm);
+    if (LOG) emit_tick(fm, tick_clk);
+    if (n_ev > 0x40000000u) { atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0; }
     seen = lead = has_bj = has_sm = rtbj = 0;
     tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
     has_ej = false;
@@ -479,17 +485,17 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
 
     // ---- advance-clock core.clj:128-135 ----
     if (live) {
-      if (tstar != clock) fired = 0;
+      if (tstar != clock) { fired = 0; tick_here = false; }
       clock = tstar;
     }
     const bool will_log = live && (p.up_down ? true : ((b_aj | b_tb | b_tm | b_st | b_us | b_bl | b_ub) != 0));
     {
-      const bool do_flush = will_log && seen != 0 && clock != tick_clk;   // push-log of the previous tick
+      const bool do_flush = will_log && seen != 0 && !tick_here;          // push-log of the previous tick
       const unsigned fm = __ballot_sync(am, do_flush);
       if (do_flush) flush_tick(fm);
-      if (will_log) tick_clk = clock;
+      if (will_log && !tick_here) { TICKCLK = clock; tick_here = true; }
     }
-    n_events += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
+    n_ev += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
                 MO::popc(b_us) + MO::popc(b_bl) + MO::popc(b_ub);
 
     // ---- run the batch in generator order, core.clj:742 ----
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_EJ, i, 0, id);
         if (has_ej) status = MJP_INST_TICK_OVERFLOW;
-        has_ej = true; ej_ent = ent;
+        has_ej = true; EJENT = ent;
       }
       occ &= ~bit;
     }
@@ -635,11 +641,13 @@ __global__ void __launch_bounds__(64) __maxnreg__(sizeof(MaskT) == 4 ? 88 : 168)
   // the reference never flushes the last tick: whatever is still in :log-buf is lost
   if (p.final_clock) p.final_clock[g] = clock;
   if (p.curjob) p.curjob[g] = (long long)curjob;
-  if (p.n_events) p.n_events[g] = n_events;
+  atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
   if (HASH && p.hash) p.hash[g] = h;
   p.status[g] = (uint8_t)status;
 #undef FUT_T
 #undef ENDS_S
+#undef TICKCLK
+#undef EJENT
 #undef CNT
 #undef BS
 #undef SS

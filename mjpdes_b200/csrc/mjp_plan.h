@@ -27,6 +27,16 @@ struct LinePlan {
 
 inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Per-thread shared-memory slots of one kernel variant (must mirror the macros in mjp_line_kernel.cuh):
+//   f64: FUT_T[M] BS[M] SS[M] LASTCLK[M-1] TICKCLK EJENT | ENDS[M] unless in registers | stage[stage_cap] if LOG
+//   u32: FUT_N[M] STARTED[M] CNT[M-1] JT[R/4] | EIDX[M] if REPLAY | ORD[stage_cap/4] if LOG
+inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log) {
+  const int M = kp.M;
+  kp.nf64 = 4 * M + 1 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
+  kp.nu32 = 3 * M - 1 + (kp.R >> 2) + (replay ? M : 0) + (log ? ((kp.stage_cap + 3) >> 2) : 0);
+  return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
+}
+
 inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   LinePlan pl;
   KParams &kp = pl.kp;
@@ -63,14 +73,9 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
     double accum = L->portion[0];
     for (int k = 0; k < K; ++k) { pl.cd.push_back(accum); accum = accum + L->portion[k]; }
   }
-  // SCADA capture stages one tick of messages per instance in shared memory (8 B each) plus their
-  // cleaned order (1 B each).  A tick holds at most a handful of messages per machine.
-  kp.stage_cap = L->log ? 3 * M + 8 : 0;
-  kp.nf64 = 5 * M - 1 + kp.stage_cap;
-  kp.nu32 = 2 * M + (M - 1) + (R >> 2) + M                 // the last M: REPLAY exponential cursors
-            + ((kp.stage_cap + 3) >> 2);
   kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
-  pl.per_thread_bytes = (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
+  kp.stage_cap = L->log ? 3 * M + 8 : 0;
+  pl.per_thread_bytes = plan_layout(kp, false, true, L->log != 0);   // the largest variant
   return pl;
 }
 

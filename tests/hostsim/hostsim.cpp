@@ -17,12 +17,14 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   kp.dur = dc + pl.off_dur(); kp.thr = dc + pl.off_thr();
   kp.N = pl.ci.data(); kp.lvl = pl.ci.data() + (M - 1);
   kp.lam_i = L->lambda_inst; kp.mu_i = L->mu_inst; kp.W_i = L->W_inst; kp.w_i = L->w_inst; kp.N_i = L->N_inst;
+  const bool want_log_early = log && L->log;
   const bool sweep = kp.lam_i || kp.mu_i || kp.W_i || kp.w_i || kp.N_i;
   std::vector<double> enters((size_t)kp.R * n_inst);
   kp.enters = enters.data();
   for (size_t q = 0; q < (size_t)M * n_inst; ++q) { s->blocked_time[q] = 0; s->starved_time[q] = 0; }
   for (size_t q = 0; q < (size_t)kp.L * n_inst; ++q) s->occ_time[q] = 0;
-  for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; }
+  for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; s->n_events[q] = 0; }
+  mjp::plan_layout(kp, !want_log_early && M >= 2 && M <= 8, rng->mode == MJP_RNG_REPLAY, want_log_early);
   kp.njobs = s->njobs; kp.residence = s->residence_sum; kp.blocked = s->blocked_time; kp.starved = s->starved_time;
   kp.occ = s->occ_time; kp.final_clock = s->final_clock; kp.curjob = s->current_job; kp.n_events = s->n_events;
   kp.hash = s->event_hash; kp.status = s->status;
