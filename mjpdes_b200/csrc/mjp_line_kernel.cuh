@@ -138,12 +138,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
   uint32_t *su = reinterpret_cast<uint32_t *>(smem_raw + p.const_bytes + (size_t)p.nf64 * nt * 8) + tid;
 #define FUT_T(i)   sf[(i) * nt]                 /* :future etime                      */
-#define BS(i)      sf[(M + (i)) * nt]           /* :bs (NaN = nil), util/log.clj:176  */
-#define SS(i)      sf[(2 * M + (i)) * nt]       /* :ss                                */
-#define LASTCLK(b) sf[(3 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
-#define TICKCLK    sf[(4 * M - 1) * nt]         /* :clk of the messages in :log-buf   */
-#define EJENT      sf[(4 * M) * nt]             /* :ent of this tick's :ej            */
-#define ENDS_S(i)  sf[(4 * M + 1 + (i)) * nt]   /* :status :ends, or remaining work (MT == 0 only) */
+#define NXT_T(i)   sf[(M + (i)) * nt]           /* etime of the event after :future (valid unless `need`) */
+#define BS(i)      sf[(2 * M + (i)) * nt]       /* :bs (NaN = nil), util/log.clj:176  */
+#define SS(i)      sf[(3 * M + (i)) * nt]       /* :ss                                */
+#define LASTCLK(b) sf[(4 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
+#define TICKCLK    sf[(5 * M - 1) * nt]         /* :clk of the messages in :log-buf   */
+#define EJENT      sf[(5 * M) * nt]             /* :ent of this tick's :ej            */
+#define ENDS_S(i)  sf[(5 * M + 1 + (i)) * nt]   /* :status :ends, or remaining work (MT == 0 only) */
 #define FUT_N(i)   su[(i) * nt]                 /* :future index                      */
 #define STARTED(i) su[(M + (i)) * nt]           /* jobs started on machine i          */
 #define CNT(b)     su[(2 * M + (b)) * nt]       /* (count :holding) of buffer b       */
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // ---- model state in registers ---------------------------------------------
   double clock = 0.0;
   MaskT occ = 0, B = 0, S = 0, full = 0, pend = 0, dup = 0, fired = 0;
+  MaskT need = ALL;                             // machines whose NXT_T has not been generated yet
   MaskT empty = ALL & ~(MaskT)1;               // feed-buffer-empty? (nil for the entry machine, utils.clj:85)
   const MaskT upj = p.jm2dm ? ALL : (MaskT)0;  // :jm2dm, core.clj:490,495
   uint32_t curjob = 0;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // ---- SCADA capture (LOG): :log-buf of the current tick, staged in shared memory ----
   // word: act | m << 8 | n << 16 | done << 31 | job << 32
   unsigned long long *s_stage =
-      reinterpret_cast<unsigned long long *>(sf + (size_t)(4 * M + 1 + (MT > 0 ? 0 : M)) * nt);
+      reinterpret_cast<unsigned long long *>(sf + (size_t)(5 * M + 1 + (MT > 0 ? 0 : M)) * nt);
   uint32_t *s_ord = s_eidx + (size_t)(REPLAY ? M : 0) * nt;   // cleaned order, 4 indices per word
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
@@ -377,18 +379,25 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   auto flush_tick = [&](const unsigned fm) {
     const double tick_clk = TICKCLK;
     const bool warm = tick_clk >= p.warm_up;                               // util/log.clj:104
-    // :bl/:ub of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed in order
-    for (MaskT q = warm ? tgB_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
-      const int i = MO::ffs(q); q &= q - 1;
-      const double bs = BS(i);
-      if (((B0 >> i) & 1) && bs == bs) red_add(p.blocked + (size_t)i * n_inst + g, tick_clk - bs);   // block-
-      BS(i) = ((B >> i) & 1) ? tick_clk : QNAN;                                                       // block+
-    }
-    for (MaskT q = warm ? tgS_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
-      const int i = MO::ffs(q); q &= q - 1;
-      const double ss = SS(i);
-      if (((S0 >> i) & 1) && ss == ss) red_add(p.starved + (size_t)i * n_inst + g, tick_clk - ss);   // starve-
-      SS(i) = ((S >> i) & 1) ? tick_clk : QNAN;                                                       // starve+
+    // :bl/:ub (and :st/:us) of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed
+    // in order, which nets to: close the interval that was open at tick start (block- / starve-), then open
+    // one iff the machine ends the tick blocked (starved).  Both kinds share one voted loop.
+    auto interval = [&](int i, bool is_s) {
+      double *slot = &sf[((is_s ? 3 : 2) * M + i) * nt];                       // SS(i) : BS(i)
+      const double t0 = *slot;
+      const bool open0 = (((is_s ? S0 : B0) >> i) & 1) != 0, open1 = (((is_s ? S : B) >> i) & 1) != 0;
+      if (open0 && t0 == t0) red_add((is_s ? p.starved : p.blocked) + (size_t)i * n_inst + g, tick_clk - t0);
+      *slot = open1 ? tick_clk : QNAN;
+    };
+    if (sizeof(MaskT) == 4) {
+      uint64_t q = warm ? ((uint64_t)tgB_lo | ((uint64_t)tgS_lo << 32)) : 0ull;
+      while (__any_sync(fm, q != 0)) if (q) {
+        const int j = __ffsll((long long)q) - 1; q &= q - 1;
+        interval(j & 31, j >= 32);
+      }
+    } else {
+      for (MaskT q = warm ? tgB_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, false); }
+      for (MaskT q = warm ? tgS_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, true); }
     }
     // buf+ / buf- (util/log.clj:159-171): the first message on a buffer in cleaned order gets the
     // elapsed time, the others add (clk - clk) = 0.
@@ -408,9 +417,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     if (warm && has_ej) {                                                    // end-job util/log.clj:212-217
       red_add(p.residence + g, tick_clk - EJENT);
       atomicAdd(reinterpret_cast<unsigned long long *>(p.njobs) + g, 1ull);
+      if (n_ev > 0x40000000u) {                               // keep the 32-bit event counter from wrapping
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0;
+      }
     }
     if (LOG) emit_tick(fm, tick_clk);
-    if (n_ev > 0x40000000u) { atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0; }
     seen = lead = has_bj = has_sm = rtbj = 0;
     tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
     has_ej = false;
@@ -450,38 +461,46 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const MaskT c_tb = occ & ~B & notfull & ~pend & ALL;       // time = max(clock, :ends)   core.clj:472-483
     const MaskT st_chk = ~S & empty & occ & ~pend;             // finished? needs clock >= :ends, utils.clj:68-74
 
-    // One fixed-trip pass over the machines (every lane does the same work): min over the timed
-    // candidates, remembering who attains it, and the finished? bits new-starved? needs.  The up/down
-    // candidates (core.clj:356-372) enter through the cached (tmin_ud, m_udc).
+    // Machines whose job is already over (clock >= :ends).  For them max(clock, :ends) = clock, so their
+    // advance2buffer candidate is a "now" candidate; a BAS new-blocked candidate that is late has
+    // :ends == clock (an occupied, unblocked BAS machine always owns a candidate at :ends, so the clock
+    // cannot pass it).  Only the strictly-future :ends need a min.
+    MaskT late = 0;
+#pragma unroll
+    for (int i = 0; i < (MT > 0 ? MT : M); ++i)
+      if (clock >= (MT > 0 ? r_end[i] : ENDS_S(i))) late |= MJP_BIT(i);
+    late &= occ & ~pend;
+    const MaskT c_st = ~S & empty & (~occ | late) & ALL;                                      // core.clj:451-460
+    const MaskT tb_now = c_tb & late, bl_now = c_bla & late, fut = (c_tb | c_bla) & ~late;
+    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup | tb_now | bl_now) != 0;
+
+    // min over the future candidates: pending up/down events (cached) and future :ends
     double tmin = tmin_ud;
-    MaskT m_ud = m_udc, m_tb = 0, m_bl = 0, fin = ~occ;
 #pragma unroll
     for (int i = 0; i < (MT > 0 ? MT : M); ++i) {
-      const MaskT bit = MJP_BIT(i);
-      const double en = MT > 0 ? r_end[i] : ENDS_S(i);
-      const bool is_tb = (c_tb & bit) != 0, is_bl = (c_bla & bit) != 0;
-      const double tj = is_tb ? fmax(clock, en) : (is_bl ? en : INF);
-      if (tj < tmin) { tmin = tj; m_ud = m_tb = m_bl = 0; }
-      if (tj == tmin) { if (is_tb) m_tb |= bit; if (is_bl) m_bl |= bit; }
-      if ((st_chk & bit) && clock >= en) fin |= bit;
+      const double e = (fut & MJP_BIT(i)) ? (MT > 0 ? r_end[i] : ENDS_S(i)) : INF;
+      tmin = e < tmin ? e : tmin;
     }
-    m_ud &= ~dup;
-    const MaskT c_st = ~S & empty & fin & ALL;                                                // core.clj:451-460
-    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup) != 0;
-    double tstar = tmin;
-    if (now_any) {
-      if (clock < tmin) { tstar = clock; m_ud = m_tb = m_bl = 0; }
-      else if (clock > tmin && live) { status = MJP_INST_CLOCK_BACK; live = false; }          // core.clj:133
+    bool live2 = live;
+    if (live && (now_any ? (tmin < clock) : (tmin == INF))) {
+      status = now_any ? MJP_INST_CLOCK_BACK : MJP_INST_NO_RUNABLES;                          // core.clj:133,739
+      live2 = false;
     }
-    if (live && tstar == INF) { status = MJP_INST_NO_RUNABLES; live = false; }
-    if (live && clock > tstar) { status = MJP_INST_CLOCK_BACK; live = false; }
-    // candidates at time `clock` are in the batch iff clock == tstar, i.e. iff now_any
-    const MaskT keep_now = (live && now_any) ? ~(MaskT)0 : (MaskT)0, keep = live ? ~(MaskT)0 : (MaskT)0;
+    live = live2;
+    const double tstar = now_any ? clock : tmin;
+    MaskT m_f = 0;                                            // future :ends equal to t*
+    if (!now_any) {
+#pragma unroll
+      for (int i = 0; i < (MT > 0 ? MT : M); ++i)
+        if ((fut & MJP_BIT(i)) && (MT > 0 ? r_end[i] : ENDS_S(i)) == tstar) m_f |= MJP_BIT(i);
+    }
+    const MaskT m_ud = (tmin_ud == tstar) ? (m_udc & ~dup) : (MaskT)0;
+    const MaskT keep = live ? ~(MaskT)0 : (MaskT)0, keep_now = (live && now_any) ? ~(MaskT)0 : (MaskT)0;
     MaskT b_aj = c_aj & keep_now;
     MaskT b_tm = c_tm & keep_now, b_st = c_st & keep_now, b_us = c_us & keep_now, b_ub = c_ub & keep_now;
-    MaskT b_bl = (m_bl & keep) | (c_blb & keep_now);
+    MaskT b_bl = ((m_f & c_bla) & keep) | ((c_blb | bl_now) & keep_now);
     MaskT b_ud = (m_ud & keep) | (dup & keep_now);
-    MaskT b_tb = m_tb & keep;
+    MaskT b_tb = ((m_f & c_tb) & keep) | (tb_now & keep_now);
 
     // ---- advance-clock core.clj:128-135 ----
     if (live) {
@@ -526,12 +545,20 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
             else {
               double rem = get_end(0), t = FUT_T(0), v;
               uint32_t n = FUT_N(0), ecur = REPLAY ? s_eidx[0] : 0u;
-              if (up & 1) { t = next_event_time(0, n, false, t, ecur); ++n; }      // the :up after the pending :down
+              bool have_nxt = !(need & 1);                     // event n+1 is already realised in NXT_T(0)
+              auto after = [&](bool prev_is_up, double t_prev) -> double {
+                double r;
+                if (have_nxt) { r = NXT_T(0); have_nxt = false; }
+                else r = next_event_time(0, n, prev_is_up, t_prev, ecur);
+                ++n;
+                return r;
+              };
+              if (up & 1) t = after(false, t);                 // the :up after the pending :down
               for (;;) {
-                const double t_dn = next_event_time(0, n, true, t, ecur); ++n;
+                const double t_dn = after(true, t);
                 if (!end_time_resume(t, t_dn, rem, v)) break;
                 rem = v;
-                t = next_event_time(0, n, false, t_dn, ecur); ++n;
+                t = after(false, t_dn);
               }
               aj_ends = v;
             }
@@ -560,9 +587,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         else {
           const double t_fire = FUT_T(i);
           const uint32_t n = FUT_N(i);
-          uint32_t ecur = REPLAY ? s_eidx[i * nt] : 0u;
-          const double t_next = next_event_time(i, n, was_up_event, t_fire, ecur);
-          if (REPLAY) s_eidx[i * nt] = ecur;
+          double t_next;
+          if (need & bit) {                                  // not pre-generated yet: do it here (rare)
+            uint32_t ecur = REPLAY ? s_eidx[i * nt] : 0u;
+            t_next = next_event_time(i, n, was_up_event, t_fire, ecur);
+            if (REPLAY) s_eidx[i * nt] = ecur;
+          } else t_next = NXT_T(i);
+          need |= bit;
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
           if (was_up_event && (pend & bit)) {                // end-time resumes at this :up  core.clj:145-151
             double v;
@@ -571,6 +602,22 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
           }
           rescan_fut();
         }
+      }
+    }
+    {
+      // Pre-generate the event AFTER each machine's pending one (core.clj:180-191), lazily: the Philox + ln
+      // path is ~200 instructions and only ~5 % of the events need it, so it runs when at least 8 lanes of
+      // the warp have something to generate (or every active lane has), not whenever one lane does.
+      const unsigned needm = __ballot_sync(am, need != 0);
+      if (__popc(needm) >= 8 || needm == am) {
+        for (MaskT q = need; __any_sync(am, q != 0);) if (q) {
+          const int i = MO::ffs(q); q &= q - 1;
+          const bool pending_is_up = !((up ^ dup) & MJP_BIT(i));
+          uint32_t ecur = REPLAY ? s_eidx[i * nt] : 0u;
+          NXT_T(i) = next_event_time(i, FUT_N(i), pending_is_up, FUT_T(i), ecur);
+          if (REPLAY) s_eidx[i * nt] = ecur;
+        }
+        need = 0;
       }
     }
     for (MaskT q = b_tb; __any_sync(am, q != 0);) if (q) {   // advance2buffer core.clj:285-300
@@ -646,6 +693,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   p.status[g] = (uint8_t)status;
 #undef FUT_T
 #undef ENDS_S
+#undef NXT_T
 #undef TICKCLK
 #undef EJENT
 #undef CNT
