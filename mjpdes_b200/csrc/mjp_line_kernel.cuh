@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define LASTCLK(b) sf[(4 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
 #define TICKCLK    sf[(5 * M - 1) * nt]         /* :clk of the messages in :log-buf   */
 #define EJENT      sf[(5 * M) * nt]             /* :ent of this tick's :ej            */
-#define ENDS_S(i)  sf[(5 * M + 1 + (i)) * nt]   /* :status :ends, or remaining work (MT == 0 only) */
+#define TMINUD     sf[(5 * M + 1) * nt]         /* earliest pending up/down time (cache) */
+#define ENDS_S(i)  sf[(5 * M + 2 + (i)) * nt]   /* :status :ends, or remaining work (MT == 0 only) */
 #define FUT_N(i)   su[(i) * nt]                 /* :future index                      */
 #define STARTED(i) su[(M + (i)) * nt]           /* jobs started on machine i          */
 #define CNT(b)     su[(2 * M + (b)) * nt]       /* (count :holding) of buffer b       */
@@ -238,15 +239,16 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   for (int b = 0; active && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
   for (int b = 0; active && b < M - 1; ++b) CNT(b) = 0u;
   // min over the machines' pending up/down times and who attains it: changes only when one fires
-  double tmin_ud = INF;
   MaskT m_udc = 0;
   auto rescan_fut = [&]() {
-    tmin_ud = INF; m_udc = 0;
+    double t0 = INF;
+    m_udc = 0;
     for (int i = 0; i < M; ++i) {
       const double t = FUT_T(i);
-      if (t < tmin_ud) { tmin_ud = t; m_udc = 0; }
-      if (t == tmin_ud) m_udc |= MJP_BIT(i);
+      if (t < t0) { t0 = t; m_udc = 0; }
+      if (t == t0) m_udc |= MJP_BIT(i);
     }
+    TMINUD = t0;
   };
   if (active) rescan_fut();
 
@@ -258,16 +260,19 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   const MaskT upj = p.jm2dm ? ALL : (MaskT)0;  // :jm2dm, core.clj:490,495
   uint32_t curjob = 0;
   uint32_t n_ev = 0;                            // run-action calls not yet added to p.n_events
-  uint32_t iters = 0;
-  const uint32_t iter_cap = p.max_iter > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)p.max_iter;
   uint64_t h = 0xcbf29ce484222325ull;
   // tick state (what :log-buf holds, util/log.clj:89-109)
-  bool tick_here = false;                       // TICKCLK == clock
   MaskT seen = 0, lead = 0, has_bj = 0, has_sm = 0, rtbj = 0;
-  MaskT tgB_lo = 0, tgB_hi = 0, tgS_lo = 0, tgS_hi = 0, B0 = 0, S0 = 0;
-  bool has_ej = false;
+  // :bl/:ub (resp. :st/:us) messages of the tick per machine: parity and "two seen".  A machine cannot
+  // toggle three times in one tick while processing times are positive (it would have to finish a job it
+  // started in the same tick); a third toggle is reported as MJP_INST_TICK_OVERFLOW.
+  MaskT pB = 0, twoB = 0, pS = 0, twoS = 0;
   // steady accumulators kept in registers
-  int status = MJP_INST_NOT_RUN;
+  // tick / loop flags share one register: F_EJ this tick has an :ej, F_TICK TICKCLK == clock,
+  // F_OVF a per-tick structure overflowed
+  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4 };
+  uint32_t flags = 0;
+  auto finish = [&](int code) { p.status[g] = (uint8_t)code; };     // the instance ends with this :status
 
   int type_cache = -2;                 // job type of the NEXT job when already drawn (-2: not drawn)
 
@@ -278,10 +283,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     lead = (lead & ~fresh) | (fresh & ~next_seen);
     seen |= bit;
   };
-  auto toggle = [&](MaskT &lo, MaskT &hi, MaskT bit) {   // saturating 2-bit counter per machine
-    const MaskT carry = lo & bit, sat = hi & lo & bit;
-    lo = (lo ^ bit) | sat;
-    hi |= carry;
+  auto toggle = [&](MaskT &par, MaskT &two, MaskT bit) {
+    if (two & bit) flags |= F_OVF;
+    two |= par & bit;
+    par ^= bit;
   };
   // new-job (core.clj:328-340): job number d+1 uses half (d & 1) of Philox block {d >> 1, consumer 0}
   auto type_from = [&](double choose) -> int {
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // ---- SCADA capture (LOG): :log-buf of the current tick, staged in shared memory ----
   // word: act | m << 8 | n << 16 | done << 31 | job << 32
   unsigned long long *s_stage =
-      reinterpret_cast<unsigned long long *>(sf + (size_t)(5 * M + 1 + (MT > 0 ? 0 : M)) * nt);
+      reinterpret_cast<unsigned long long *>(sf + (size_t)(5 * M + 2 + (MT > 0 ? 0 : M)) * nt);
   uint32_t *s_ord = s_eidx + (size_t)(REPLAY ? M : 0) * nt;   // cleaned order, 4 indices per word
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     if (n_staged < stage_cap)
       s_stage[n_staged * nt] = (unsigned long long)act | ((unsigned long long)m << 8) |
                                ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);
-    else status = MJP_INST_TICK_OVERFLOW;
+    else flags |= F_OVF;
     n_staged++;
   };
   // clean-log-buf (util/log.clj:38-57) + print-lines (util/log.clj:111-137): order the staged messages,
@@ -385,19 +390,20 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     auto interval = [&](int i, bool is_s) {
       double *slot = &sf[((is_s ? 3 : 2) * M + i) * nt];                       // SS(i) : BS(i)
       const double t0 = *slot;
-      const bool open0 = (((is_s ? S0 : B0) >> i) & 1) != 0, open1 = (((is_s ? S : B) >> i) & 1) != 0;
+      // exactly one message of this kind in the tick (two cancel, util/log.clj:51-53): the state flipped
+      const bool open1 = (((is_s ? S : B) >> i) & 1) != 0, open0 = !open1;
       if (open0 && t0 == t0) red_add((is_s ? p.starved : p.blocked) + (size_t)i * n_inst + g, tick_clk - t0);
       *slot = open1 ? tick_clk : QNAN;
     };
     if (sizeof(MaskT) == 4) {
-      uint64_t q = warm ? ((uint64_t)tgB_lo | ((uint64_t)tgS_lo << 32)) : 0ull;
+      uint64_t q = warm ? ((uint64_t)pB | ((uint64_t)pS << 32)) : 0ull;
       while (__any_sync(fm, q != 0)) if (q) {
         const int j = __ffsll((long long)q) - 1; q &= q - 1;
         interval(j & 31, j >= 32);
       }
     } else {
-      for (MaskT q = warm ? tgB_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, false); }
-      for (MaskT q = warm ? tgS_lo : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, true); }
+      for (MaskT q = warm ? pB : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, false); }
+      for (MaskT q = warm ? pS : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, true); }
     }
     // buf+ / buf- (util/log.clj:159-171): the first message on a buffer in cleaned order gets the
     // elapsed time, the others add (clk - clk) = 0.
@@ -414,18 +420,21 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
       LASTCLK(b) = tick_clk;
     }
-    if (warm && has_ej) {                                                    // end-job util/log.clj:212-217
-      red_add(p.residence + g, tick_clk - EJENT);
-      atomicAdd(reinterpret_cast<unsigned long long *>(p.njobs) + g, 1ull);
-      if (n_ev > 0x40000000u) {                               // keep the 32-bit event counter from wrapping
+    if (flags & F_EJ) {
+      if (warm) {                                             // end-job util/log.clj:212-217
+        red_add(p.residence + g, tick_clk - EJENT);
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.njobs) + g, 1ull);
+      }
+      // n_ev counts the events since it was last folded into p.n_events; it is folded whenever a job has
+      // left the line, so 3e9 events without a single exit means the instance is stuck (watchdog above)
+      if (n_ev > 0x40000000u) {
         atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0;
       }
     }
     if (LOG) emit_tick(fm, tick_clk);
     seen = lead = has_bj = has_sm = rtbj = 0;
-    tgB_lo = tgB_hi = tgS_lo = tgS_hi = 0;
-    has_ej = false;
-    B0 = B; S0 = S;
+    pB = twoB = pS = twoS = 0;
+    flags &= ~(uint32_t)F_EJ;
   };
   // end-time at job start (core.clj:138-151), lazily: fits in the current up interval, or pending
   auto start_job = [&](int i, int type) {
@@ -447,8 +456,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     bool live = true;
     // end-main-loop? core.clj:722-727
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
-      status = MJP_INST_NORMAL_END; live = false;
-    } else if (++iters == iter_cap) { status = MJP_INST_ITER_LIMIT; live = false; }
+      finish(MJP_INST_NORMAL_END); live = false;
+    } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -475,6 +484,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup | tb_now | bl_now) != 0;
 
     // min over the future candidates: pending up/down events (cached) and future :ends
+    const double tmin_ud = TMINUD;
     double tmin = tmin_ud;
 #pragma unroll
     for (int i = 0; i < (MT > 0 ? MT : M); ++i) {
@@ -483,7 +493,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
     bool live2 = live;
     if (live && (now_any ? (tmin < clock) : (tmin == INF))) {
-      status = now_any ? MJP_INST_CLOCK_BACK : MJP_INST_NO_RUNABLES;                          // core.clj:133,739
+      finish(now_any ? MJP_INST_CLOCK_BACK : MJP_INST_NO_RUNABLES);                           // core.clj:133,739
       live2 = false;
     }
     live = live2;
@@ -504,15 +514,15 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 
     // ---- advance-clock core.clj:128-135 ----
     if (live) {
-      if (tstar != clock) { fired = 0; tick_here = false; }
+      if (tstar != clock) { fired = 0; flags &= ~(uint32_t)F_TICK; }
       clock = tstar;
     }
     const bool will_log = live && (p.up_down ? true : ((b_aj | b_tb | b_tm | b_st | b_us | b_bl | b_ub) != 0));
     {
-      const bool do_flush = will_log && seen != 0 && !tick_here;          // push-log of the previous tick
+      const bool do_flush = will_log && seen != 0 && !(flags & F_TICK);   // push-log of the previous tick
       const unsigned fm = __ballot_sync(am, do_flush);
       if (do_flush) flush_tick(fm);
-      if (will_log && !tick_here) { TICKCLK = clock; tick_here = true; }
+      if (will_log && !(flags & F_TICK)) { TICKCLK = clock; flags |= F_TICK; }
     }
     n_ev += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
                 MO::popc(b_us) + MO::popc(b_bl) + MO::popc(b_ub);
@@ -530,7 +540,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
           else { type = type_from(u0); type_cache = type_from(u1); }
         }
         if (type < 0) {                                      // the reference dies in job-requires
-          status = MJP_INST_JOBTYPE_NIL; live = false;
+          finish(MJP_INST_JOBTYPE_NIL); live = false;
           b_ud = b_tb = b_tm = b_st = b_us = b_bl = b_ub = 0;
         } else {
           const uint32_t id = curjob + 1;
@@ -573,9 +583,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     {                                                        // bring-machine-up, then -down: core.clj:215-238
       MaskT q_up = b_ud & ~up, q_dn = b_ud & up;
       while (__any_sync(am, (q_up | q_dn) != 0)) if (q_up | q_dn) {
-        MaskT &q = q_up ? q_up : q_dn;
-        const int i = MO::ffs(q); q &= q - 1;
-        const MaskT bit = MJP_BIT(i);
+        const bool from_up = q_up != 0;                      // (no reference-select: it would pin both masks in local memory)
+        const MaskT qq = from_up ? q_up : q_dn;
+        const MaskT bit = qq & (~qq + 1);
+        const int i = MO::ffs(qq);
+        q_up &= from_up ? ~bit : ~(MaskT)0;
+        q_dn &= from_up ? ~(MaskT)0 : ~bit;
         const bool was_up_event = !(up & bit);
         if (HASH) {
           hmix(h, (uint64_t)(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN) | ((uint64_t)i << 8));
@@ -629,7 +642,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
-        if (has_bj & bit) status = MJP_INST_TICK_OVERFLOW;
+        if (has_bj & bit) flags |= F_OVF;
         has_bj |= bit;
         rtbj |= bit & ~has_sm;
         CNT(i) = (uint32_t)(n + 1);
@@ -640,8 +653,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_EJ, i, 0, id);
-        if (has_ej) status = MJP_INST_TICK_OVERFLOW;
-        has_ej = true; EJENT = ent;
+        if (flags & F_EJ) flags |= F_OVF;
+        flags |= F_EJ; EJENT = ent;
       }
       occ &= ~bit;
     }
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);
       if (LOG) stage_msg(MJP_ACT_SM, i, n, id);
-      if (has_sm & bbit) status = MJP_INST_TICK_OVERFLOW;
+      if (has_sm & bbit) flags |= F_OVF;
       has_sm |= bbit;
       CNT(b) = (uint32_t)(n - 1);
       if (n - 1 == 0) empty |= bit;
@@ -668,18 +681,22 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       MaskT q_st = b_st, q_us = b_us, q_bl = b_bl, q_ub = b_ub;   // new-starved, -unstarved, -blocked, -unblocked
       while (__any_sync(am, (q_st | q_us | q_bl | q_ub) != 0)) if (q_st | q_us | q_bl | q_ub) {
         const int which = q_st ? 0 : (q_us ? 1 : (q_bl ? 2 : 3));
-        MaskT &q = which == 0 ? q_st : (which == 1 ? q_us : (which == 2 ? q_bl : q_ub));
-        const int i = MO::ffs(q); q &= q - 1;
-        const MaskT bit = MJP_BIT(i);
+        const MaskT qq = which == 0 ? q_st : (which == 1 ? q_us : (which == 2 ? q_bl : q_ub));
+        const MaskT bit = qq & (~qq + 1);
+        const int i = MO::ffs(qq);
+        q_st &= which == 0 ? ~bit : ~(MaskT)0;
+        q_us &= which == 1 ? ~bit : ~(MaskT)0;
+        q_bl &= which == 2 ? ~bit : ~(MaskT)0;
+        q_ub &= which == 3 ? ~bit : ~(MaskT)0;
         if (HASH) { hmix(h, (uint64_t)(MJP_ACT_ST + which) | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_ST + which, i, 0, 0u);
-        if (which < 2) { S ^= bit; toggle(tgS_lo, tgS_hi, bit); }
-        else { B ^= bit; toggle(tgB_lo, tgB_hi, bit); }
+        if (which < 2) { S ^= bit; toggle(pS, twoS, bit); }
+        else { B ^= bit; toggle(pB, twoB, bit); }
       }
     }
-    if (status == MJP_INST_TICK_OVERFLOW) live = false;
-    else if (live && seen == 0) { status = MJP_INST_LOGBUF_EMPTY; live = false; }   // push-log returned nil, util/log.clj:95
+    if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW); live = false; }
+    else if (live && seen == 0) { finish(MJP_INST_LOGBUF_EMPTY); live = false; }    // push-log returned nil, util/log.clj:95
     active = live;
     }
   }
@@ -690,9 +707,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   if (p.curjob) p.curjob[g] = (long long)curjob;
   atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
   if (HASH && p.hash) p.hash[g] = h;
-  p.status[g] = (uint8_t)status;
 #undef FUT_T
 #undef ENDS_S
+#undef TMINUD
 #undef NXT_T
 #undef TICKCLK
 #undef EJENT

@@ -28,11 +28,11 @@ struct LinePlan {
 inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Per-thread shared-memory slots of one kernel variant (must mirror the macros in mjp_line_kernel.cuh):
-//   f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1] TICKCLK EJENT | ENDS[M] unless in registers | stage[stage_cap] if LOG
+//   f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1] TICKCLK EJENT TMINUD | ENDS[M] unless in registers | stage[stage_cap] if LOG
 //   u32: FUT_N[M] STARTED[M] CNT[M-1] JT[R/4] | EIDX[M] if REPLAY | ORD[stage_cap/4] if LOG
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log) {
   const int M = kp.M;
-  kp.nf64 = 5 * M + 1 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
+  kp.nf64 = 5 * M + 2 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
   kp.nu32 = 3 * M - 1 + (kp.R >> 2) + (replay ? M : 0) + (log ? ((kp.stage_cap + 3) >> 2) : 0);
   return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
 }
@@ -60,7 +60,7 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
     for (int i = 0; i < M; ++i) rate += 4.0 + L->lambda[i] + L->mu[i];
     double it = 512.0 * (L->run_to + 1.0) * rate + 1e6;
     if (L->run_to_job >= 0) it += 64.0 * (double)L->run_to_job * M;
-    kp.max_iter = it > 9e18 ? (uint64_t)9e18 : (uint64_t)it;
+    kp.max_iter = it > 4.29e9 ? 0xFFFFFFFFull : (uint64_t)it;      // the kernel counts iterations in 32 bits
   }
   pl.cd.insert(pl.cd.end(), L->lambda, L->lambda + M);
   pl.cd.insert(pl.cd.end(), L->mu, L->mu + M);
