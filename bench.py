@@ -273,7 +273,8 @@ def main():
         if im:
             ach = per_gpu_rate * im["warp_inst_per_event"] / 1e9
             out["roofline"] = {"bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s",
-                               "frac": ach / peak, "traffic": im.get("dram_bytes_per_launch"),
+                               "frac": ach / peak,
+                               "traffic": im.get("dram_bytes_per_event", 0.0) * events_per_step / world,
                                "warp_inst_per_event": im["warp_inst_per_event"],
                                "lane_efficiency": im.get("lane_efficiency"),
                                "peak_source": "148 SMs x 4 SMSPs x clocks.max.sm (SURVEY 8d); warp-inst/event from "

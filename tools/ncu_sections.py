@@ -25,12 +25,12 @@ def main():
     src = open(SRC).read().splitlines()
     find = lambda s: next(i + 1 for i, l in enumerate(src) if s in l)
     marks = [("prologue/init", 1), ("loop head + guard masks", find("for (;;) {")),
-             ("scan (min candidate time)", find("One fixed-trip pass over the machines")),
-             ("t*, batch masks", find("m_ud &= ~dup;")), ("clock + flush vote", find("// ---- advance-clock")),
+             ("scan (min candidate time)", find("Machines whose job is already over")),
+             ("t*, batch masks", find("const MaskT m_ud = (tmin_ud == tstar)")), ("clock + flush vote", find("// ---- advance-clock")),
              ("AJ section", find("if (__any_sync(am, b_aj != 0))")), ("UP/DOWN section", find("bring-machine-up, then -down")),
              ("TOBUF section", find("// advance2buffer core.clj:285-300")), ("TOMACH section", find("// advance2machine core.clj:263-277")),
              ("record-actions section", find("record-actions core.clj:304-326, in the order")),
-             ("loop tail", find("if (status == MJP_INST_TICK_OVERFLOW) live = false;"))]
+             ("loop tail", find("if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW)"))]
     helpers = [("flush_tick", find("auto flush_tick"), find("auto start_job")),
                ("SCADA stage/emit", find("auto stage_msg"), find("// push-log for the tick that just ended")),
                ("byte get/set, params", find("auto getb"), find("double r_end[")),
