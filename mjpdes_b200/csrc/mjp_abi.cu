@@ -50,7 +50,7 @@ struct mjp_handle {
   mjp::KParams kp{};
   std::vector<int32_t> Ncap;
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage, d_cold;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -119,9 +119,9 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   return MJP_OK;
 }
 
-template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
+template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG, bool COLD>
 static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int threads, size_t smem, cudaStream_t st) {
-  auto k = mjp::mjp_line_kernel<MaskT, MT, REPLAY, HASH, SWEEP, LOG>;
+  auto k = mjp::mjp_line_kernel<MaskT, MT, REPLAY, HASH, SWEEP, LOG, COLD>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<blocks, threads, smem, st>>>(kp);
@@ -129,12 +129,12 @@ static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int thread
 }
 
 // MT > 0 (register-resident :ends, exactly MT machines) exists without SCADA capture only.
-template <typename MaskT, int MT>
+template <typename MaskT, int MT, bool COLD = false>
 static cudaError_t launch_flags(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
                                 int threads, size_t smem, cudaStream_t st) {
   const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
 #define MJP_CASE(n, LG) \
-  case n: return launch_variant<MaskT, MT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, LG>(kp, blocks, threads, smem, st);
+  case n: return launch_variant<MaskT, MT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, LG, COLD>(kp, blocks, threads, smem, st);
   if constexpr (MT == 0) {
     if (log) {
       switch (v) {
@@ -155,9 +155,10 @@ static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
   return !log && !force_generic && threads == MJP_FIXED_NT && kp.M >= 2 && kp.M <= 8;
 }
 
-static cudaError_t launch_line_kernel(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
-                                      int threads, size_t smem, cudaStream_t st) {
+static cudaError_t launch_line_kernel(bool replay, bool hash, bool sweep, bool log, bool cold, const mjp::KParams &kp,
+                                      int blocks, int threads, size_t smem, cudaStream_t st) {
 #define MJP_ARGS replay, hash, sweep, log, kp, blocks, threads, smem, st
+  if (cold) return kp.M > 32 ? launch_flags<uint64_t, 0, true>(MJP_ARGS) : launch_flags<uint32_t, 0, true>(MJP_ARGS);
   if (kp.M > 32) return launch_flags<uint64_t, 0>(MJP_ARGS);
   if (use_register_ends(kp, log, threads)) {
     switch (kp.M) {
@@ -216,7 +217,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_stage})
+                    &h->d_logcur, &h->d_stage, &h->d_cold})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -349,11 +350,25 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
   const bool replay = rng->mode == MJP_RNG_REPLAY, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
   if (h->want_log && !kp.log_records) return fail(h, MJP_ERR_INVALID, "SCADA capture wanted: call mjp_reserve_log first");
   {
-    const int threads = h->block_threads;
+    int threads = h->block_threads;
     const bool mt = use_register_ends(kp, h->want_log, threads);
-    h->smem_bytes = (size_t)kp.const_bytes + mjp::plan_layout(kp, mt, replay, h->want_log) * threads;
+    size_t per_thread = mjp::plan_layout(kp, mt, replay, h->want_log, false);
+    // Wide lines: when shared memory would hold fewer than 6 CTAs of 64 threads per SM, keep only the
+    // per-micro-step state on chip and the rest in an L2-resident scratch (COLD variants).
+    static const char *cold_env = std::getenv("MJP_COLD");            // A/B measurements: 0 = never, 1 = always
+    bool cold = !mt && (size_t)kp.const_bytes + per_thread * 64 + 1024 > h->smem_optin / 6;
+    if (cold_env) cold = !mt && cold_env[0] == '1';
+    if (cold) {
+      threads = 64;
+      per_thread = mjp::plan_layout(kp, false, replay, h->want_log, true);
+      const size_t fb = mjp::plan_align_up((size_t)mjp::cold_f64_slots(kp) * kp.n_inst * 8, 256);
+      CK(h->d_cold.reserve(fb + (size_t)mjp::cold_u32_slots(kp, replay) * kp.n_inst * 4));
+      kp.cold_f = h->d_cold.as<double>();
+      kp.cold_u = reinterpret_cast<uint32_t *>((char *)h->d_cold.ptr + fb);
+    }
+    h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
-    cudaError_t e = launch_line_kernel(replay, hash, h->sweep, h->want_log, kp, blocks, threads, h->smem_bytes, h->stream);
+    cudaError_t e = launch_line_kernel(replay, hash, h->sweep, h->want_log, cold, kp, blocks, threads, h->smem_bytes, h->stream);
     CK(e);
     launches++;
   }

@@ -110,7 +110,9 @@ __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid, uint64
 
 // MT > 0: the line has exactly MT machines and their :ends live in registers (fully unrolled scan);
 // MT == 0: any M, :ends in shared memory.
-template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG>
+// COLD (wide lines): everything that is not read every micro-step lives in an L2-resident scratch
+// [slot][instance] instead of shared memory, so that enough warps fit on an SM.
+template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG, bool COLD = false>
 __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -134,32 +136,37 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
   bool active = g < n_inst;
 
-  // ---- per-thread state in shared memory: [slot][thread] -------------------
+  // ---- per-instance state: [slot][thread] in shared memory; the cold part optionally in global ----
   double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
   uint32_t *su = reinterpret_cast<uint32_t *>(smem_raw + p.const_bytes + (size_t)p.nf64 * nt * 8) + tid;
-#define FUT_T(i)   sf[(i) * nt]                 /* :future etime                      */
-#define NXT_T(i)   sf[(M + (i)) * nt]           /* etime of the event after :future (valid unless `need`) */
-#define BS(i)      sf[(2 * M + (i)) * nt]       /* :bs (NaN = nil), util/log.clj:176  */
-#define SS(i)      sf[(3 * M + (i)) * nt]       /* :ss                                */
-#define LASTCLK(b) sf[(4 * M + (b)) * nt]       /* :lastclk, util/log.clj:151,164     */
-#define TICKCLK    sf[(5 * M - 1) * nt]         /* :clk of the messages in :log-buf   */
-#define EJENT      sf[(5 * M) * nt]             /* :ent of this tick's :ej            */
-#define TMINUD     sf[(5 * M + 1) * nt]         /* earliest pending up/down time (cache) */
-#define ENDS_S(i)  sf[(5 * M + 2 + (i)) * nt]   /* :status :ends, or remaining work (MT == 0 only) */
-#define FUT_N(i)   su[(i) * nt]                 /* :future index                      */
-#define STARTED(i) su[(M + (i)) * nt]           /* jobs started on machine i          */
-#define CNT(b)     su[(2 * M + (b)) * nt]       /* (count :holding) of buffer b       */
-  uint32_t *s_jt = su + (size_t)(3 * M - 1) * nt;                 /* job type ring, 4 per word    */
-  uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * nt;              /* REPLAY only: exponential cursor */
+  double *cfp = COLD ? p.cold_f + g : sf;                   // cold f64 slots and their stride
+  uint32_t *cup = COLD ? p.cold_u + g : su;
+  const size_t cs = COLD ? (size_t)n_inst : (size_t)nt;
+  const int hb = COLD ? 0 : 5 * M - 1;                     // first hot f64 slot in shared memory
+  const int hu = COLD ? 0 : 2 * M;                         // first hot u32 slot in shared memory
+#define FUT_T(i)   cfp[(i) * cs]                 /* :future etime                      */
+#define NXT_T(i)   cfp[(M + (i)) * cs]           /* etime of the event after :future (valid unless `need`) */
+#define BS(i)      cfp[(2 * M + (i)) * cs]       /* :bs (NaN = nil), util/log.clj:176  */
+#define SS(i)      cfp[(3 * M + (i)) * cs]       /* :ss                                */
+#define LASTCLK(b) cfp[(4 * M + (b)) * cs]       /* :lastclk, util/log.clj:151,164     */
+#define TICKCLK    sf[(hb) * nt]                /* :clk of the messages in :log-buf   */
+#define EJENT      sf[(hb + 1) * nt]            /* :ent of this tick's :ej            */
+#define TMINUD     sf[(hb + 2) * nt]            /* earliest pending up/down time (cache) */
+#define ENDS_S(i)  sf[(hb + 3 + (i)) * nt]      /* :status :ends, or remaining work (MT == 0 only) */
+#define FUT_N(i)   cup[(i) * cs]                 /* :future index                      */
+#define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
+#define CNT(b)     su[(hu + (b)) * nt]          /* (count :holding) of buffer b       */
+  uint32_t *s_jt = cup + (size_t)(COLD ? 2 * M : 3 * M - 1) * cs;  /* job type ring, 4 per word    */
+  uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * cs;              /* REPLAY only: exponential cursor */
   const uint32_t Rm = (uint32_t)p.R - 1;
 
-  auto getb = [&](uint32_t *base, int idx) -> uint32_t {
-    return (base[(idx >> 2) * nt] >> ((idx & 3) * 8)) & 0xFFu;
+  auto getb = [&](uint32_t *base, size_t stride, int idx) -> uint32_t {
+    return (base[(idx >> 2) * stride] >> ((idx & 3) * 8)) & 0xFFu;
   };
-  auto setb = [&](uint32_t *base, int idx, uint32_t v) {
+  auto setb = [&](uint32_t *base, size_t stride, int idx, uint32_t v) {
     const int sh = (idx & 3) * 8;
-    uint32_t wd = base[(idx >> 2) * nt];
-    base[(idx >> 2) * nt] = (wd & ~(0xFFu << sh)) | (v << sh);
+    uint32_t wd = base[(idx >> 2) * stride];
+    base[(idx >> 2) * stride] = (wd & ~(0xFFu << sh)) | (v << sh);
   };
   // line parameters, with the optional per-instance planes
   auto lam_of = [&](int i) -> double { return (SWEEP && p.lam_i) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       uint32_t o2[4];
       px(0u, 2u + 2u * i, o2);
       eu = u52open(o2[0], o2[1]);
-      s_eidx[i * nt] = 1u;
+      s_eidx[i * cs] = 1u;
     } else {
       eu = u52open(o[2], o[3]);
     }
@@ -296,8 +303,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // ---- SCADA capture (LOG): :log-buf of the current tick, staged in shared memory ----
   // word: act | m << 8 | n << 16 | done << 31 | job << 32
   unsigned long long *s_stage =
-      reinterpret_cast<unsigned long long *>(sf + (size_t)(5 * M + 2 + (MT > 0 ? 0 : M)) * nt);
-  uint32_t *s_ord = s_eidx + (size_t)(REPLAY ? M : 0) * nt;   // cleaned order, 4 indices per word
+      reinterpret_cast<unsigned long long *>(sf + (size_t)(hb + 3 + (MT > 0 ? 0 : M)) * nt);
+  // cleaned order, 4 indices per word: after the hot u32 slots (and the cold ones when they share the array)
+  uint32_t *s_ord = su + (size_t)(COLD ? M - 1 : 3 * M - 1 + (p.R >> 2) + (REPLAY ? M : 0)) * nt;
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
   uint32_t line_cnt = 0;                                   // [:report :line-cnt]
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
             const int cc = (act == MJP_ACT_BL || act == MJP_ACT_UB) ? 0 : ((act == MJP_ACT_ST || act == MJP_ACT_US) ? 1 : 2);
             if (cc != c) continue;
             s_stage[b * nt] = wb | (1ull << 31);
-            if (!drop) { setb(s_ord, k, (uint32_t)b); ++k; }
+            if (!drop) { setb(s_ord, (size_t)nt, k, (uint32_t)b); ++k; }
           }
         }
       }
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       mjp_log_record *out = reinterpret_cast<mjp_log_record *>(p.log_records);
       unsigned dropped = 0;
       for (int q = 0; q < k; ++q) {
-        const unsigned long long w = s_stage[getb(s_ord, q) * nt];
+        const unsigned long long w = s_stage[getb(s_ord, (size_t)nt, q) * nt];
         const unsigned long long at = base + prefix + q;
         if (at >= p.log_capacity) { ++dropped; continue; }
         const int act = (int)(w & 0xFF);
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     // in order, which nets to: close the interval that was open at tick start (block- / starve-), then open
     // one iff the machine ends the tick blocked (starved).  Both kinds share one voted loop.
     auto interval = [&](int i, bool is_s) {
-      double *slot = &sf[((is_s ? 3 : 2) * M + i) * nt];                       // SS(i) : BS(i)
+      double *slot = &cfp[((is_s ? 3 : 2) * M + i) * cs];                       // SS(i) : BS(i)
       const double t0 = *slot;
       // exactly one message of this kind in the tick (two cancel, util/log.clj:51-53): the state flipped
       const bool open1 = (((is_s ? S : B) >> i) & 1) != 0, open0 = !open1;
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
             }
           }
           curjob = id; occ |= 1; STARTED(0) = id;
-          setb(s_jt, (int)(id & Rm), (uint32_t)type);
+          setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
           p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
           if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
         }
@@ -602,9 +610,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
           const uint32_t n = FUT_N(i);
           double t_next;
           if (need & bit) {                                  // not pre-generated yet: do it here (rare)
-            uint32_t ecur = REPLAY ? s_eidx[i * nt] : 0u;
+            uint32_t ecur = REPLAY ? s_eidx[i * cs] : 0u;
             t_next = next_event_time(i, n, was_up_event, t_fire, ecur);
-            if (REPLAY) s_eidx[i * nt] = ecur;
+            if (REPLAY) s_eidx[i * cs] = ecur;
           } else t_next = NXT_T(i);
           need |= bit;
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
@@ -626,9 +634,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         for (MaskT q = need; __any_sync(am, q != 0);) if (q) {
           const int i = MO::ffs(q); q &= q - 1;
           const bool pending_is_up = !((up ^ dup) & MJP_BIT(i));
-          uint32_t ecur = REPLAY ? s_eidx[i * nt] : 0u;
+          uint32_t ecur = REPLAY ? s_eidx[i * cs] : 0u;
           NXT_T(i) = next_event_time(i, FUT_N(i), pending_is_up, FUT_T(i), ecur);
-          if (REPLAY) s_eidx[i * nt] = ecur;
+          if (REPLAY) s_eidx[i * cs] = ecur;
         }
         need = 0;
       }
@@ -664,7 +672,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       const int b = i - 1;
       const int n = (int)CNT(b);
       const uint32_t id = STARTED(i) + 1;
-      const int type = (int)getb(s_jt, (int)(id & Rm));
+      const int type = (int)getb(s_jt, cs, (int)(id & Rm));
       start_job(i, type);
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);

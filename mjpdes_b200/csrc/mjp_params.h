@@ -30,6 +30,8 @@ struct KParams {
   int64_t *curjob; uint64_t *n_events; uint64_t *hash; uint8_t *status;
   // scratch
   double *enters;         // [R][n_inst] :enters of the jobs in the line
+  double *cold_f;         // COLD variants: [5M-1][n_inst]  FUT_T NXT_T BS SS LASTCLK
+  uint32_t *cold_u;       // COLD variants: [2M + R/4 + M][n_inst]  FUT_N STARTED JT EIDX
   // SCADA records
   void *log_records;      // mjp_log_record[log_capacity]
   uint64_t log_capacity;

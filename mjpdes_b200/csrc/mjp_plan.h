@@ -28,12 +28,17 @@ struct LinePlan {
 inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Per-thread shared-memory slots of one kernel variant (must mirror the macros in mjp_line_kernel.cuh):
-//   f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1] TICKCLK EJENT TMINUD | ENDS[M] unless in registers | stage[stage_cap] if LOG
-//   u32: FUT_N[M] STARTED[M] CNT[M-1] JT[R/4] | EIDX[M] if REPLAY | ORD[stage_cap/4] if LOG
-inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log) {
+//   cold f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1]         cold u32: FUT_N[M] STARTED[M] JT[R/4] EIDX[M] if REPLAY
+//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] unless in registers | stage[stage_cap] if LOG
+//   hot  u32: CNT[M-1] | ORD[stage_cap/4] if LOG
+// Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX ORD);
+// with it they live in a global scratch of cold_f64_slots / cold_u32_slots rows per instance.
+inline int cold_f64_slots(const KParams &kp) { return 5 * kp.M - 1; }
+inline int cold_u32_slots(const KParams &kp, bool replay) { return 2 * kp.M + (kp.R >> 2) + (replay ? kp.M : 0); }
+inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
-  kp.nf64 = 5 * M + 2 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
-  kp.nu32 = 3 * M - 1 + (kp.R >> 2) + (replay ? M : 0) + (log ? ((kp.stage_cap + 3) >> 2) : 0);
+  kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
+  kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1) + (log ? ((kp.stage_cap + 3) >> 2) : 0);
   return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
 }
 

@@ -7,7 +7,7 @@
 #include <vector>
 
 extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
-                           int want_hash, mjp_log_out *log) {
+                           int want_hash, mjp_log_out *log, int force_cold) {
   mjp::LinePlan pl = mjp::build_plan(L, n_inst);
   mjp::KParams kp = pl.kp;
   const int M = kp.M;
@@ -24,7 +24,12 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   for (size_t q = 0; q < (size_t)M * n_inst; ++q) { s->blocked_time[q] = 0; s->starved_time[q] = 0; }
   for (size_t q = 0; q < (size_t)kp.L * n_inst; ++q) s->occ_time[q] = 0;
   for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; s->n_events[q] = 0; }
-  mjp::plan_layout(kp, !want_log_early && M >= 2 && M <= 8, rng->mode == MJP_RNG_REPLAY, want_log_early);
+  const bool cold = force_cold != 0;
+  const bool mt_ok = !cold && !want_log_early && M >= 2 && M <= 8;
+  mjp::plan_layout(kp, mt_ok, rng->mode == MJP_RNG_REPLAY, want_log_early, cold);
+  std::vector<double> coldf((size_t)mjp::cold_f64_slots(kp) * n_inst);
+  std::vector<uint32_t> coldu((size_t)mjp::cold_u32_slots(kp, true) * n_inst);
+  kp.cold_f = coldf.data(); kp.cold_u = coldu.data();
   kp.njobs = s->njobs; kp.residence = s->residence_sum; kp.blocked = s->blocked_time; kp.starved = s->starved_time;
   kp.occ = s->occ_time; kp.final_clock = s->final_clock; kp.curjob = s->current_job; kp.n_events = s->n_events;
   kp.hash = s->event_hash; kp.status = s->status;
@@ -46,7 +51,20 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
     else if (sweep) mjp::mjp_line_kernel<MK, MT, false, false, true, LG>(kp); \
     else mjp::mjp_line_kernel<MK, MT, false, false, false, LG>(kp);
     // the same dispatch as launch_line_kernel in mjp_abi.cu
-    if (M > 32) { if (want_log) { RUN3(uint64_t, 0, true) } else { RUN3(uint64_t, 0, false) } }
+#define RUNC(MK, LG) \
+    if (replay && hash && sweep) mjp::mjp_line_kernel<MK, 0, true, true, true, LG, true>(kp); \
+    else if (replay && hash) mjp::mjp_line_kernel<MK, 0, true, true, false, LG, true>(kp); \
+    else if (replay && sweep) mjp::mjp_line_kernel<MK, 0, true, false, true, LG, true>(kp); \
+    else if (replay) mjp::mjp_line_kernel<MK, 0, true, false, false, LG, true>(kp); \
+    else if (hash && sweep) mjp::mjp_line_kernel<MK, 0, false, true, true, LG, true>(kp); \
+    else if (hash) mjp::mjp_line_kernel<MK, 0, false, true, false, LG, true>(kp); \
+    else if (sweep) mjp::mjp_line_kernel<MK, 0, false, false, true, LG, true>(kp); \
+    else mjp::mjp_line_kernel<MK, 0, false, false, false, LG, true>(kp);
+    if (cold) {
+      if (M > 32) { if (want_log) { RUNC(uint64_t, true) } else { RUNC(uint64_t, false) } }
+      else { if (want_log) { RUNC(uint32_t, true) } else { RUNC(uint32_t, false) } }
+    }
+    else if (M > 32) { if (want_log) { RUN3(uint64_t, 0, true) } else { RUN3(uint64_t, 0, false) } }
     else if (want_log) { RUN3(uint32_t, 0, true) }
     else switch (M) {
       case 2: RUN3(uint32_t, 2, false) break;

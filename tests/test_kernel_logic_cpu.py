@@ -79,3 +79,22 @@ def test_aggregate_matches_oracle(oracle):
     a, b = H.run(line, 7, seed=9), oracle.run(line, 7, seed=9).stats
     assert a.aggregate[0] == 7
     assert np.allclose(a.aggregate, b.aggregate, rtol=1e-12)
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_cold_state_layout(oracle, trial):
+    """COLD variants (wide lines): the cold per-instance state lives in a global scratch instead of shared
+    memory; same results bit for bit."""
+    rng = np.random.default_rng(500 + trial)
+    M = [3, 10, 20, 33, 50, 64][trial]
+    line = random_line(rng, M, int(rng.integers(1, 5)), run_to=150.0, warm_up=15.0, up_down=bool(trial % 2))
+    mode = MODES[trial % 2]
+    assert_same(H.run(line, 3, mode=mode, seed=trial, cold=True), oracle.run(line, 3, mode=mode, seed=trial).stats)
+
+
+def test_cold_state_layout_with_scada_log(oracle):
+    line = mixed20_line(warm_up=20, run_to=200)
+    want = oracle.run(line, 2, seed=SEED, log_capacity=100_000)
+    got = H.run(line, 2, seed=SEED, log_capacity=100_000, cold=True)
+    a, b = np.sort(got.log, order=["instance", "line"]), np.sort(want.log, order=["instance", "line"])
+    assert len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in ("clk", "job", "line", "n", "act", "machine"))
