@@ -356,7 +356,11 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
     // Wide lines: when shared memory would hold fewer than 6 CTAs of 64 threads per SM, keep only the
     // per-micro-step state on chip and the rest in an L2-resident scratch (COLD variants).
     static const char *cold_env = std::getenv("MJP_COLD");            // A/B measurements: 0 = never, 1 = always
-    bool cold = !mt && (size_t)kp.const_bytes + per_thread * 64 + 1024 > h->smem_optin / 6;
+    // ... but only when the batch is large enough to need the extra residency (otherwise it only adds latency)
+    const size_t cta_bytes = (size_t)kp.const_bytes + per_thread * threads + 1024;
+    const size_t resident = (size_t)(h->sm_count > 0 ? h->sm_count : 148) * (h->smem_optin / cta_bytes);
+    bool cold = !mt && (size_t)kp.const_bytes + per_thread * 64 + 1024 > h->smem_optin / 6 &&
+                (kp.n_inst + threads - 1) / threads > resident;
     if (cold_env) cold = !mt && cold_env[0] == '1';
     if (cold) {
       threads = 64;

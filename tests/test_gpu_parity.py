@@ -186,3 +186,16 @@ def test_c2_full_size_properties(engine):
     assert np.isclose(agg[1], tp.sum(), rtol=1e-12) and np.isclose(agg[2], (tp * tp).sum(), rtol=1e-12)
     assert np.isclose(agg[5], (s.blocked_time[0] / run_time).sum(), rtol=1e-12)
     assert len(np.unique(s.event_hash)) == n              # every replication is a different realisation
+
+
+@pytest.mark.parametrize("M,K,n,run_to", [(50, 16, 12032, 100.0), (10, 1, 50048, 100.0)])
+def test_cold_layout_variants_on_device(engine, oracle, M, K, n, run_to):
+    """Batches of wide lines that do not fit one wave with all state in shared memory switch to the COLD
+    variants (cold per-instance state in an L2-resident scratch, mjp_abi.cu): same results bit for bit."""
+    if M == 50:
+        line = long50_line(warm_up=10.0, run_to=run_to)
+    else:
+        line = sweep10_line(n, warm_up=10.0, run_to=run_to, first=7)
+    got = engine.run(line, n, seed=SEED)
+    want = oracle.run(line, n, seed=SEED, n_threads=8)
+    assert_same(got.stats, want.stats)

@@ -52,6 +52,9 @@ def main():
         out["C4_mixed20_stats_only"] = timed(h, mixed20_line(warm_up=2000, run_to=20000, log=False), 16384)
         out["C5_long50_slice"] = timed(h, long50_line(warm_up=2000, run_to=20000), 9472)
         out["C5_long50_slice"]["note"] = "M=50, K=16; time-boxed slice (run-to 2e4, not 1e6), 9472 = 148 x 64 instances"
+        out["C4_mixed20_stats_many"] = timed(h, mixed20_line(warm_up=2000, run_to=6000, log=False), 75776, reps=1)
+        out["C5_long50_many"] = timed(h, long50_line(warm_up=2000, run_to=5000), 37888, reps=1)
+        out["C5_long50_many"]["note"] = "M=50, K=16; 37888 instances, run-to 5000: enough instances to need more than one wave without the COLD layout"
         out["example2"] = timed(h, example2_line(), 104192)
         out["submodel1"] = timed(h, submodel1_line(), 104192)
     print(json.dumps(out, indent=1))
