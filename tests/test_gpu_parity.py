@@ -199,3 +199,16 @@ def test_cold_layout_variants_on_device(engine, oracle, M, K, n, run_to):
     got = engine.run(line, n, seed=SEED)
     want = oracle.run(line, n, seed=SEED, n_threads=8)
     assert_same(got.stats, want.stats)
+
+
+def test_run_to_job_and_all_override_planes(engine, oracle):
+    line = example_line(run_to=300.0, warm_up=30.0, run_to_job=600)
+    assert_same(engine.run(line, 70, seed=11).stats, oracle.run(line, 70, seed=11, n_threads=8).stats)
+    rng = np.random.default_rng(42)
+    n, M, K = 90, 4, 2
+    line = abi.HostLine(lam=[.1] * M, mu=[.9] * M, W=[1.] * M, discipline=[0, 1, 0, 0], N=[4, 4, 4], portion=[.5, .5],
+                        w=np.ones((K, M)), warm_up=20, run_to=400,
+                        lam_inst=rng.uniform(0.05, 0.2, (M, n)), mu_inst=rng.uniform(0.5, 1.5, (M, n)),
+                        W_inst=rng.uniform(0.8, 1.2, (M, n)), N_inst=rng.integers(1, 5, (M - 1, n)),
+                        w_inst=rng.uniform(0.5, 1.5, (K * M, n)))
+    assert_same(engine.run(line, n, seed=2).stats, oracle.run(line, n, seed=2, n_threads=8).stats)

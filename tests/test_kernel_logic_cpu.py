@@ -98,3 +98,25 @@ def test_cold_state_layout_with_scada_log(oracle):
     got = H.run(line, 2, seed=SEED, log_capacity=100_000, cold=True)
     a, b = np.sort(got.log, order=["instance", "line"]), np.sort(want.log, order=["instance", "line"])
     assert len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in ("clk", "job", "line", "n", "act", "machine"))
+
+
+def test_run_to_job_keeps_the_loop_going(oracle):
+    """end-main-loop? (core.clj:722-727): the loop continues while current-job <= :run-to-job OR clock <= :run-to-time."""
+    line = example_line(run_to=200.0, warm_up=20.0, run_to_job=400)
+    a, b = H.run(line, 4, seed=11), oracle.run(line, 4, seed=11).stats
+    assert_same(a, b)
+    assert np.all(b.current_job > 400) and np.all(b.final_clock > 200.0)
+    short = oracle.run(example_line(run_to=200.0, warm_up=20.0), 4, seed=11).stats
+    assert np.all(short.current_job < 400)
+
+
+def test_per_instance_capacity_and_rate_planes(oracle):
+    """All five override planes at once (lambda, mu, W, N, w per instance)."""
+    rng = np.random.default_rng(42)
+    n, M, K = 6, 4, 2
+    line = abi.HostLine(lam=[.1] * M, mu=[.9] * M, W=[1.] * M, discipline=[0, 1, 0, 0], N=[4, 4, 4], portion=[.5, .5],
+                        w=np.ones((K, M)), warm_up=20, run_to=400,
+                        lam_inst=rng.uniform(0.05, 0.2, (M, n)), mu_inst=rng.uniform(0.5, 1.5, (M, n)),
+                        W_inst=rng.uniform(0.8, 1.2, (M, n)), N_inst=rng.integers(1, 5, (M - 1, n)),
+                        w_inst=rng.uniform(0.5, 1.5, (K * M, n)))
+    assert_same(H.run(line, n, seed=2), oracle.run(line, n, seed=2).stats)
