@@ -120,3 +120,20 @@ def test_per_instance_capacity_and_rate_planes(oracle):
                         W_inst=rng.uniform(0.8, 1.2, (M, n)), N_inst=rng.integers(1, 5, (M - 1, n)),
                         w_inst=rng.uniform(0.5, 1.5, (K * M, n)))
     assert_same(H.run(line, n, seed=2), oracle.run(line, n, seed=2).stats)
+
+
+def test_kernel_source_under_address_and_ub_sanitizers(tmp_path):
+    """compute-sanitizer is closed on the GPU pool; the kernel source runs under ASan + UBSan on the host
+    instead (tests/hostsim/asan_main.cpp): every plane is an exact-size heap buffer and the unused tail of
+    the shared-memory arena is poisoned, so a wrong slot offset or plane index traps."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+    exe = str(tmp_path / "asan_main")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fsanitize=address,undefined",
+                           "-fno-sanitize-recover=undefined", "-o", exe, os.path.join(here, "asan_main.cpp")])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and "asan run clean" in out.stdout, out.stdout[-2000:]
