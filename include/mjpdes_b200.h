@@ -51,6 +51,7 @@ enum {
   MJP_INST_TICK_OVERFLOW= 5,  /* device-only: more same-clock messages than the staging
                                  area holds; instance stopped, statistics invalid     */
   MJP_INST_ITER_LIMIT   = 6,  /* device-only: watchdog on loop iterations tripped        */
+  MJP_INST_PAUSED       = 7,  /* mjp_launch_slice(): parked at the slice boundary, resumable  */
   MJP_INST_NOT_RUN      = 255
 };
 
@@ -212,6 +213,12 @@ int mjp_reserve_log(mjp_handle *h, uint64_t capacity);
 int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log);  /* async on the handle's stream */
 int mjp_sync(mjp_handle *h);
 int mjp_download(mjp_handle *h, mjp_stats_out *stats, mjp_log_out *log);
+/* Time-sliced run (long horizons, streaming): advance every instance until its clock passes `until` (or the
+ * run ends), park its complete state in HBM and return; call again with resume = 1 and a later `until` to
+ * continue.  Slicing is invisible in the results: statistics, event hash and SCADA records are those of one
+ * uninterrupted run.  Instances parked report MJP_INST_PAUSED.  SCADA records of each slice start at the
+ * beginning of the record buffer (download them between slices).                                          */
+int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, double until, int resume);
 /* milliseconds between the CUDA events bracketing the last mjp_launch()'s kernels */
 int mjp_last_kernel_ms(mjp_handle *h, float *ms);
 /* number of kernels launched by the last mjp_launch() */

@@ -17,6 +17,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, LOG_TRUNCATED = range(6)
 # per-instance status  ([:params :status], core.clj:735,739)
 INST_NORMAL_END, INST_NO_RUNABLES, INST_CLOCK_BACK, INST_JOBTYPE_NIL, INST_LOGBUF_EMPTY, INST_TICK_OVERFLOW = range(6)
+INST_ITER_LIMIT, INST_PAUSED = 6, 7
 INST_NOT_RUN = 255
 INST_STATUS_KEYWORD = {
     INST_NORMAL_END: ":normal-end",
@@ -25,6 +26,8 @@ INST_STATUS_KEYWORD = {
     INST_JOBTYPE_NIL: ":jobtype-nil",
     INST_LOGBUF_EMPTY: ":log-buf-empty",
     INST_TICK_OVERFLOW: ":tick-overflow",
+    INST_ITER_LIMIT: ":iteration-limit",
+    INST_PAUSED: ":paused",
     INST_NOT_RUN: ":not-run",
 }
 # actions
@@ -240,6 +243,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.mjp_upload.argtypes = [H, C.POINTER(LineDesc), C.c_uint64]
     lib.mjp_reserve_log.argtypes = [H, C.c_uint64]
     lib.mjp_launch.argtypes = [H, C.POINTER(RngSpec), C.c_int]
+    lib.mjp_launch_slice.argtypes = [H, C.POINTER(RngSpec), C.c_int, C.c_double, C.c_int]
     lib.mjp_sync.argtypes = [H]
     lib.mjp_download.argtypes = [H, C.POINTER(StatsOut), C.POINTER(LogOut)]
     lib.mjp_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float)]
@@ -254,6 +258,6 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "mjp_abi_version", "mjp_device_count", "mjp_aggregate_len", "mjp_create", "mjp_destroy", "mjp_last_error",
-    "mjp_run", "mjp_upload", "mjp_reserve_log", "mjp_launch", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
+    "mjp_run", "mjp_upload", "mjp_reserve_log", "mjp_launch", "mjp_launch_slice", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
     "mjp_last_launch_count", "mjp_probe_end_time",
 ]

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -50,7 +51,7 @@ struct mjp_handle {
   mjp::KParams kp{};
   std::vector<int32_t> Ncap;
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage, d_cold;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage, d_cold, d_park;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -217,7 +218,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_stage, &h->d_cold})
+                    &h->d_logcur, &h->d_stage, &h->d_cold, &h->d_park})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -333,8 +334,14 @@ int mjp_reserve_log(mjp_handle *h, uint64_t capacity) {
 }
 
 int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
+  return mjp_launch_slice(h, rng, want_log, std::numeric_limits<double>::infinity(), 0);
+}
+
+int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, double until, int resume) {
   if (!h) return MJP_ERR_INVALID;
   if (!h->uploaded) return fail(h, MJP_ERR_INVALID, "mjp_launch before mjp_upload");
+  if (resume && !h->launched) return fail(h, MJP_ERR_INVALID, "resume without a previous sliced launch");
+  if (!(until == until)) return fail(h, MJP_ERR_INVALID, "slice boundary is NaN");
   if (!rng || (rng->mode != MJP_RNG_COUNTER && rng->mode != MJP_RNG_REPLAY))
     return fail(h, MJP_ERR_INVALID, "bad mjp_rng_spec");
   CK(cudaSetDevice(h->device));
@@ -343,8 +350,12 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
   kp.first_id = rng->first_instance_id;
   h->want_log = want_log && kp.log_on;
   int launches = 0;
-  CK(cudaMemsetAsync(h->d_out.ptr, 0, h->zero_bytes, h->stream));
-  CK(cudaMemsetAsync((char *)h->d_out.ptr + h->o_status, MJP_INST_NOT_RUN, kp.n_inst, h->stream));
+  kp.slice_until = until;
+  kp.resume = resume ? 1 : 0;
+  if (!resume) {                                  // a resumed slice keeps accumulating into the same planes
+    CK(cudaMemsetAsync(h->d_out.ptr, 0, h->zero_bytes, h->stream));
+    CK(cudaMemsetAsync((char *)h->d_out.ptr + h->o_status, MJP_INST_NOT_RUN, kp.n_inst, h->stream));
+  }
   CK(cudaMemsetAsync(h->d_logcur.ptr, 0, 16, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   const bool replay = rng->mode == MJP_RNG_REPLAY, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
@@ -371,6 +382,11 @@ int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
       kp.cold_u = reinterpret_cast<uint32_t *>((char *)h->d_cold.ptr + fb);
     }
     h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
+    if (resume || until < std::numeric_limits<double>::infinity()) {
+      kp.park_words = 72 + 2 * kp.nf64 + kp.nu32;     // loop-carried registers (<= 72 words) + every shared slot
+      CK(h->d_park.reserve((size_t)kp.park_words * kp.n_inst * 4));
+      kp.park = h->d_park.as<uint32_t>();
+    }
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
     cudaError_t e = launch_line_kernel(replay, hash, h->sweep, h->want_log, cold, kp, blocks, threads, h->smem_bytes, h->stream);
     CK(e);

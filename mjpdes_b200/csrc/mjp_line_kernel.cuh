@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   const uint32_t n_inst = (uint32_t)p.n_inst;
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
   bool active = g < n_inst;
+  // A resumed launch continues exactly the instances that were parked at the previous slice boundary.
+  const bool resume = p.resume != 0;
+  if (resume && active && p.status[g] != MJP_INST_PAUSED) active = false;
+  const bool fresh_start = active && !resume;
+  const bool ran = active;                      // this lane simulates an instance in this launch
 
   // ---- per-instance state: [slot][thread] in shared memory; the cold part optionally in global ----
   double *sf = reinterpret_cast<double *>(smem_raw + p.const_bytes) + tid;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 
   // ---- preprocess-model: first up/down event of each machine (core.clj:156-160,557-562) ----
   MaskT up = 0;
-  for (int i = 0; active && i < M; ++i) {
+  for (int i = 0; fresh_start && i < M; ++i) {
     const double lam = lam_of(i), mu = mu_of(i);
     const double p_up = __ddiv_rn(mu, __dadd_rn(lam, mu));
     uint32_t o[4];
@@ -243,8 +248,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     SS(i) = QNAN;
     if (is_up) up |= MJP_BIT(i);
   }
-  for (int b = 0; active && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
-  for (int b = 0; active && b < M - 1; ++b) CNT(b) = 0u;
+  for (int b = 0; fresh_start && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
+  for (int b = 0; fresh_start && b < M - 1; ++b) CNT(b) = 0u;
   // min over the machines' pending up/down times and who attains it: changes only when one fires
   MaskT m_udc = 0;
   auto rescan_fut = [&]() {
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
     TMINUD = t0;
   };
-  if (active) rescan_fut();
+  if (fresh_start) rescan_fut();
 
   // ---- model state in registers ---------------------------------------------
   double clock = 0.0;
@@ -452,6 +457,34 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     set_end(i, v);
   };
 
+  // ---- time slicing: the complete per-instance state, parked in HBM as [word][instance] ----
+  // One routine moves every loop-carried variable and every shared-memory slot in a fixed order, so saving
+  // and restoring cannot disagree.  (COLD state and the :enters ring already live in global memory.)
+  auto park_io = [&](const bool save) {
+    uint32_t *ps = p.park + g;
+    size_t wd = 0;
+    auto io32 = [&](uint32_t &v) { if (save) ps[wd * n_inst] = v; else v = ps[wd * n_inst]; ++wd; };
+    auto io64 = [&](uint64_t &v) {
+      uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+      io32(lo); io32(hi);
+      v = (uint64_t)lo | ((uint64_t)hi << 32);
+    };
+    auto iod = [&](double &v) { uint64_t b = d2bits(v); io64(b); v = bits2d(b); };
+    auto iom = [&](MaskT &v) { if (sizeof(MaskT) == 8) { uint64_t b = (uint64_t)v; io64(b); v = (MaskT)b; } else { uint32_t b = (uint32_t)v; io32(b); v = (MaskT)b; } };
+    iod(clock); iod(aj_ends);
+#pragma unroll
+    for (int j = 0; j < (MT > 0 ? MT : 0); ++j) iod(r_end[j]);
+    iom(up); iom(occ); iom(B); iom(S); iom(full); iom(empty); iom(pend); iom(dup); iom(fired); iom(need);
+    iom(seen); iom(lead); iom(has_bj); iom(has_sm); iom(rtbj); iom(pB); iom(twoB); iom(pS); iom(twoS); iom(m_udc);
+    uint32_t tc = (uint32_t)type_cache, ns = (uint32_t)n_staged;
+    io32(curjob); io32(n_ev); io32(flags); io32(tc); io32(line_cnt); io32(ns);
+    type_cache = (int)tc; n_staged = (int)ns;
+    io64(h);
+    for (int k = 0; k < p.nf64; ++k) iod(sf[(size_t)k * nt]);
+    for (int k = 0; k < p.nu32; ++k) io32(su[(size_t)k * nt]);
+  };
+  if (resume && active) park_io(false);
+
   // ======================= main-loop-loop, core.clj:729-744 =======================
   // One micro-step per trip with the warp in lock-step.  Nothing leaves the body early: a lane that
   // ends (or errs) empties its batch and rides along to the bottom, so every section can be a loop
@@ -466,6 +499,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
       finish(MJP_INST_NORMAL_END); live = false;
     } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
+    else if (clock > p.slice_until) {                        // slice boundary: park between two micro-steps
+      atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0;
+      park_io(true);
+      finish(MJP_INST_PAUSED); live = false;
+    }
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -629,16 +667,17 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       // Pre-generate the event AFTER each machine's pending one (core.clj:180-191), lazily: the Philox + ln
       // path is ~200 instructions and only ~5 % of the events need it, so it runs when at least 8 lanes of
       // the warp have something to generate (or every active lane has), not whenever one lane does.
-      const unsigned needm = __ballot_sync(am, need != 0);
+      const MaskT need_l = live ? need : (MaskT)0;           // (a lane that has just parked or ended touches nothing)
+      const unsigned needm = __ballot_sync(am, need_l != 0);
       if (__popc(needm) >= 8 || needm == am) {
-        for (MaskT q = need; __any_sync(am, q != 0);) if (q) {
+        for (MaskT q = need_l; __any_sync(am, q != 0);) if (q) {
           const int i = MO::ffs(q); q &= q - 1;
           const bool pending_is_up = !((up ^ dup) & MJP_BIT(i));
           uint32_t ecur = REPLAY ? s_eidx[i * cs] : 0u;
           NXT_T(i) = next_event_time(i, FUT_N(i), pending_is_up, FUT_T(i), ecur);
           if (REPLAY) s_eidx[i * cs] = ecur;
         }
-        need = 0;
+        if (live) need = 0;
       }
     }
     for (MaskT q = b_tb; __any_sync(am, q != 0);) if (q) {   // advance2buffer core.clj:285-300
@@ -708,7 +747,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     active = live;
     }
   }
-  if (g >= n_inst) return;
+  if (!ran) return;
 
   // the reference never flushes the last tick: whatever is still in :log-buf is lost
   if (p.final_clock) p.final_clock[g] = clock;

@@ -32,6 +32,11 @@ struct KParams {
   double *enters;         // [R][n_inst] :enters of the jobs in the line
   double *cold_f;         // COLD variants: [5M-1][n_inst]  FUT_T NXT_T BS SS LASTCLK
   uint32_t *cold_u;       // COLD variants: [2M + R/4 + M][n_inst]  FUT_N STARTED JT EIDX
+  // time slicing
+  double slice_until;     // park every instance whose clock has passed this (+inf: run to the end)
+  int32_t resume;         // 1: continue the instances parked by the previous launch
+  int32_t park_words;     // rows of `park`
+  uint32_t *park;         // [park_words][n_inst] parked per-instance state
   // SCADA records
   void *log_records;      // mjp_log_record[log_capacity]
   uint64_t log_capacity;

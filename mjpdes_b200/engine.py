@@ -100,6 +100,13 @@ class Handle:
         rng = abi.RngSpec(mode, 0, seed, first_instance_id)
         self._check(self._lib.mjp_launch(self._h, C.byref(rng), int(want_log)))
 
+    def launch_slice(self, until: float, resume: bool, mode: int = abi.RNG_COUNTER, seed: int = 0,
+                     first_instance_id: int = 0, want_log: bool = False):
+        """Advance every instance until its clock passes ``until`` (or the run ends) and park it in HBM;
+        ``resume=True`` continues the instances parked by the previous slice."""
+        rng = abi.RngSpec(mode, 0, seed, first_instance_id)
+        self._check(self._lib.mjp_launch_slice(self._h, C.byref(rng), int(want_log), float(until), int(resume)))
+
     def sync(self):
         self._check(self._lib.mjp_sync(self._h))
 

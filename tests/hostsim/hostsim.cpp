@@ -4,10 +4,12 @@
 #include "../../mjpdes_b200/csrc/mjp_line_kernel.cuh"
 #include "../../mjpdes_b200/csrc/mjp_plan.h"
 
+#include <limits>
 #include <vector>
 
-extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
-                           int want_hash, mjp_log_out *log, int force_cold) {
+// One launch per slice boundary in `slices` (then one to the end), resuming the parked state each time.
+extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
+                                  int want_hash, mjp_log_out *log, int force_cold, const double *slices, int n_slices) {
   mjp::LinePlan pl = mjp::build_plan(L, n_inst);
   mjp::KParams kp = pl.kp;
   const int M = kp.M;
@@ -21,6 +23,7 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   const bool sweep = kp.lam_i || kp.mu_i || kp.W_i || kp.w_i || kp.N_i;
   std::vector<double> enters((size_t)kp.R * n_inst);
   kp.enters = enters.data();
+  for (size_t q = 0; q < n_inst; ++q) s->status[q] = MJP_INST_NOT_RUN;
   for (size_t q = 0; q < (size_t)M * n_inst; ++q) { s->blocked_time[q] = 0; s->starved_time[q] = 0; }
   for (size_t q = 0; q < (size_t)kp.L * n_inst; ++q) s->occ_time[q] = 0;
   for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; s->n_events[q] = 0; }
@@ -38,7 +41,13 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
   unsigned long long cursor[2] = {0, 0};
   const bool want_log = log && L->log;
   if (want_log) { kp.log_records = log->records; kp.log_capacity = log->capacity; kp.log_cursor = cursor; }
+  kp.park_words = 72 + 2 * kp.nf64 + kp.nu32;
+  std::vector<uint32_t> park((size_t)kp.park_words * n_inst);
+  kp.park = park.data();
   gridDim.x = (unsigned)n_inst;
+  for (int sl = 0; sl <= n_slices; ++sl) {
+  kp.slice_until = sl < n_slices ? slices[sl] : std::numeric_limits<double>::infinity();
+  kp.resume = sl > 0;
   for (uint64_t g = 0; g < n_inst; ++g) {
     blockIdx.x = (unsigned)g;
 #define RUN3(MK, MT, LG) \
@@ -77,6 +86,7 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
       default: RUN3(uint32_t, 0, false) break;
     }
   }
+  }
   if (log) {
     log->count = cursor[0] < log->capacity ? cursor[0] : log->capacity;
     log->dropped = cursor[1];
@@ -89,6 +99,11 @@ extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rn
     for (int q = 0; q < len; ++q) s->aggregate[q] = partials[q];
   }
   return MJP_OK;
+}
+
+extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
+                           int want_hash, mjp_log_out *log, int force_cold) {
+  return hostsim_run_sliced(L, n_inst, rng, s, want_hash, log, force_cold, nullptr, 0);
 }
 
 extern "C" double hostsim_end_time(const uint8_t *kinds, const double *times, int n, double clock, double dur) {

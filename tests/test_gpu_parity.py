@@ -212,3 +212,22 @@ def test_run_to_job_and_all_override_planes(engine, oracle):
                         W_inst=rng.uniform(0.8, 1.2, (M, n)), N_inst=rng.integers(1, 5, (M - 1, n)),
                         w_inst=rng.uniform(0.5, 1.5, (K * M, n)))
     assert_same(engine.run(line, n, seed=2).stats, oracle.run(line, n, seed=2, n_threads=8).stats)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_time_slicing_on_device(engine, oracle, mode):
+    """mjp_launch_slice: park at slice boundaries, resume, and end with the results of one uninterrupted run."""
+    for line, n in ((example_line(run_to=900.0, warm_up=90.0), 300),
+                    (random_line(np.random.default_rng(10), 40, 2, run_to=200.0, warm_up=20.0), 70)):
+        engine.upload(line, n)
+        resume = False
+        for until in (0.0, 37.5, 37.5, 120.0, 333.3, 899.0, 5000.0, float("inf")):
+            engine.launch_slice(until, resume, mode=mode, seed=21, first_instance_id=5)
+            engine.sync()
+            resume = True
+            st = engine.download_fields(("status",)).status
+            if until < 100.0:
+                assert np.all(st == abi.INST_PAUSED)
+        got = engine.download().stats
+        want = oracle.run(line, n, mode=mode, seed=21, first_instance_id=5, n_threads=8).stats
+        assert_same(got, want)

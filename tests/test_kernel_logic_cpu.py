@@ -137,3 +137,28 @@ def test_kernel_source_under_address_and_ub_sanitizers(tmp_path):
                            "-fno-sanitize-recover=undefined", "-o", exe, os.path.join(here, "asan_main.cpp")])
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert out.returncode == 0 and "asan run clean" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("cold", [False, True])
+def test_time_slicing_is_invisible(oracle, mode, cold):
+    """mjp_launch_slice: parking the complete instance state at arbitrary slice boundaries and resuming gives
+    the results of one uninterrupted run, bit for bit (statistics, event hash, SCADA records)."""
+    slices = [0.0, 37.5, 37.5, 120.0, 121.0, 333.3, 800.0, 5000.0]      # repeated and past-the-end boundaries too
+    for line in (example_line(run_to=900.0, warm_up=90.0),
+                 random_line(np.random.default_rng(9), 11, 3, run_to=500.0, warm_up=50.0, up_down=True),
+                 random_line(np.random.default_rng(10), 40, 2, run_to=200.0, warm_up=20.0)):
+        want = oracle.run(line, 3, mode=mode, seed=21).stats
+        assert_same(H.run(line, 3, mode=mode, seed=21, cold=cold, slices=slices), want)
+
+
+def test_time_slicing_with_scada_log(oracle):
+    line = example_line(run_to=600.0, warm_up=60.0, log=True, up_down=True, max_lines=abi.UINT64_MAX)
+    want = oracle.run(line, 2, mode=abi.RNG_REPLAY, seed=5, log_capacity=100_000)
+    got = H.run(line, 2, mode=abi.RNG_REPLAY, seed=5, log_capacity=100_000, slices=[50.0, 61.0, 300.0, 599.9])
+    a, b = np.sort(got.log, order=["instance", "line"]), np.sort(want.log, order=["instance", "line"])
+    assert len(a) == len(b)
+    for f in ("clk", "job", "line", "n", "act", "machine"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(a["aux"].view(np.uint64), b["aux"].view(np.uint64))
+    assert_same(got, want.stats)
