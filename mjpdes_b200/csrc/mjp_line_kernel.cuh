@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // steady accumulators kept in registers
   // tick / loop flags share one register: F_EJ this tick has an :ej, F_TICK TICKCLK == clock,
   // F_OVF a per-tick structure overflowed
-  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4 };
+  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8 };   // F_PAUSE: stopped at a slice boundary
   uint32_t flags = 0;
   auto finish = [&](int code) { p.status[g] = (uint8_t)code; };     // the instance ends with this :status
 
@@ -460,30 +460,59 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // ---- time slicing: the complete per-instance state, parked in HBM as [word][instance] ----
   // One routine moves every loop-carried variable and every shared-memory slot in a fixed order, so saving
   // and restoring cannot disagree.  (COLD state and the :enters ring already live in global memory.)
-  auto park_io = [&](const bool save) {
+  // (Values are passed and returned, never referenced: taking the address of a loop-carried variable would
+  // pin it in local memory for the whole kernel.)
+#define MJP_PARK_LIST(D, MK, U, Q)                                                                          \
+  D(clock)                                                                                                  \
+  MK(up) MK(occ) MK(B) MK(S) MK(full) MK(empty) MK(pend) MK(dup) MK(fired) MK(need)                         \
+  MK(seen) MK(lead) MK(has_bj) MK(has_sm) MK(rtbj) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc)                \
+  U(curjob) U(n_ev) U(flags) U(type_cache)
+  // state that exists only in some variants (parking it unconditionally would keep it alive everywhere)
+#define MJP_PARK_LOG(D, U) D(aj_ends) U(line_cnt) U(n_staged)
+  auto park_save = [&]() {
     uint32_t *ps = p.park + g;
     size_t wd = 0;
-    auto io32 = [&](uint32_t &v) { if (save) ps[wd * n_inst] = v; else v = ps[wd * n_inst]; ++wd; };
-    auto io64 = [&](uint64_t &v) {
-      uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-      io32(lo); io32(hi);
-      v = (uint64_t)lo | ((uint64_t)hi << 32);
-    };
-    auto iod = [&](double &v) { uint64_t b = d2bits(v); io64(b); v = bits2d(b); };
-    auto iom = [&](MaskT &v) { if (sizeof(MaskT) == 8) { uint64_t b = (uint64_t)v; io64(b); v = (MaskT)b; } else { uint32_t b = (uint32_t)v; io32(b); v = (MaskT)b; } };
-    iod(clock); iod(aj_ends);
+    auto w32 = [&](uint32_t v) { ps[wd * n_inst] = v; ++wd; };
+    auto w64 = [&](uint64_t v) { w32((uint32_t)v); w32((uint32_t)(v >> 32)); };
+#define PD(x) w64(d2bits(x));
+#define PM(x) if (sizeof(MaskT) == 8) w64((uint64_t)(x)); else w32((uint32_t)(x));
+#define PU(x) w32((uint32_t)(x));
+#define PQ(x) w64((uint64_t)(x));
+    MJP_PARK_LIST(PD, PM, PU, PQ)
+    if (LOG) { MJP_PARK_LOG(PD, PU) }
+    if (HASH) { PQ(h) }
+#undef PD
+#undef PM
+#undef PU
+#undef PQ
 #pragma unroll
-    for (int j = 0; j < (MT > 0 ? MT : 0); ++j) iod(r_end[j]);
-    iom(up); iom(occ); iom(B); iom(S); iom(full); iom(empty); iom(pend); iom(dup); iom(fired); iom(need);
-    iom(seen); iom(lead); iom(has_bj); iom(has_sm); iom(rtbj); iom(pB); iom(twoB); iom(pS); iom(twoS); iom(m_udc);
-    uint32_t tc = (uint32_t)type_cache, ns = (uint32_t)n_staged;
-    io32(curjob); io32(n_ev); io32(flags); io32(tc); io32(line_cnt); io32(ns);
-    type_cache = (int)tc; n_staged = (int)ns;
-    io64(h);
-    for (int k = 0; k < p.nf64; ++k) iod(sf[(size_t)k * nt]);
-    for (int k = 0; k < p.nu32; ++k) io32(su[(size_t)k * nt]);
+    for (int j = 0; j < (MT > 0 ? MT : 0); ++j) w64(d2bits(r_end[j]));
+    for (int k = 0; k < p.nf64; ++k) w64(d2bits(sf[(size_t)k * nt]));
+    for (int k = 0; k < p.nu32; ++k) w32(su[(size_t)k * nt]);
   };
-  if (resume && active) park_io(false);
+  if (resume && active) {
+    const uint32_t *ps = p.park + g;
+    size_t wd = 0;
+    auto r32 = [&]() -> uint32_t { const uint32_t v = ps[wd * n_inst]; ++wd; return v; };
+    auto r64 = [&]() -> uint64_t { const uint64_t lo = r32(); const uint64_t hi = r32(); return lo | (hi << 32); };
+#define GD(x) x = bits2d(r64());
+#define GM(x) x = (MaskT)(sizeof(MaskT) == 8 ? r64() : (uint64_t)r32());
+#define GU(x) x = (decltype(x))r32();
+#define GQ(x) x = r64();
+    MJP_PARK_LIST(GD, GM, GU, GQ)
+    if (LOG) { MJP_PARK_LOG(GD, GU) }
+    if (HASH) { GQ(h) }
+#undef GD
+#undef GM
+#undef GU
+#undef GQ
+#pragma unroll
+    for (int j = 0; j < (MT > 0 ? MT : 0); ++j) r_end[j] = bits2d(r64());
+    for (int k = 0; k < p.nf64; ++k) sf[(size_t)k * nt] = bits2d(r64());
+    for (int k = 0; k < p.nu32; ++k) su[(size_t)k * nt] = r32();
+  }
+#undef MJP_PARK_LIST
+#undef MJP_PARK_LOG
 
   // ======================= main-loop-loop, core.clj:729-744 =======================
   // One micro-step per trip with the warp in lock-step.  Nothing leaves the body early: a lane that
@@ -499,11 +528,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
       finish(MJP_INST_NORMAL_END); live = false;
     } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
-    else if (clock > p.slice_until) {                        // slice boundary: park between two micro-steps
-      atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0;
-      park_io(true);
-      finish(MJP_INST_PAUSED); live = false;
-    }
+    else if (clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -748,11 +773,17 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
   }
   if (!ran) return;
+  atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
+  n_ev = 0;
+  if (flags & F_PAUSE) {                          // park the untouched state (the lane idled since the boundary)
+    flags &= ~(uint32_t)F_PAUSE;
+    park_save();
+    finish(MJP_INST_PAUSED);
+  }
 
   // the reference never flushes the last tick: whatever is still in :log-buf is lost
   if (p.final_clock) p.final_clock[g] = clock;
   if (p.curjob) p.curjob[g] = (long long)curjob;
-  atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
   if (HASH && p.hash) p.hash[g] = h;
 #undef FUT_T
 #undef ENDS_S
