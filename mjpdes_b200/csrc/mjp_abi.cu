@@ -120,9 +120,9 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   return MJP_OK;
 }
 
-template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG, bool COLD>
+template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SLICE, bool LOG, bool COLD>
 static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int threads, size_t smem, cudaStream_t st) {
-  auto k = mjp::mjp_line_kernel<MaskT, MT, REPLAY, HASH, SWEEP, LOG, COLD>;
+  auto k = mjp::mjp_line_kernel<MaskT, MT, REPLAY, HASH, SLICE, LOG, COLD>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<blocks, threads, smem, st>>>(kp);
@@ -131,9 +131,9 @@ static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int thread
 
 // MT > 0 (register-resident :ends, exactly MT machines) exists without SCADA capture only.
 template <typename MaskT, int MT, bool COLD = false>
-static cudaError_t launch_flags(bool replay, bool hash, bool sweep, bool log, const mjp::KParams &kp, int blocks,
+static cudaError_t launch_flags(bool replay, bool hash, bool slice, bool log, const mjp::KParams &kp, int blocks,
                                 int threads, size_t smem, cudaStream_t st) {
-  const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (sweep ? 1 : 0);
+  const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (slice ? 1 : 0);
 #define MJP_CASE(n, LG) \
   case n: return launch_variant<MaskT, MT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, LG, COLD>(kp, blocks, threads, smem, st);
   if constexpr (MT == 0) {
@@ -156,9 +156,9 @@ static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
   return !log && !force_generic && threads == MJP_FIXED_NT && kp.M >= 2 && kp.M <= 8;
 }
 
-static cudaError_t launch_line_kernel(bool replay, bool hash, bool sweep, bool log, bool cold, const mjp::KParams &kp,
+static cudaError_t launch_line_kernel(bool replay, bool hash, bool slice, bool log, bool cold, const mjp::KParams &kp,
                                       int blocks, int threads, size_t smem, cudaStream_t st) {
-#define MJP_ARGS replay, hash, sweep, log, kp, blocks, threads, smem, st
+#define MJP_ARGS replay, hash, slice, log, kp, blocks, threads, smem, st
   if (cold) return kp.M > 32 ? launch_flags<uint64_t, 0, true>(MJP_ARGS) : launch_flags<uint32_t, 0, true>(MJP_ARGS);
   if (kp.M > 32) return launch_flags<uint64_t, 0>(MJP_ARGS);
   if (use_register_ends(kp, log, threads)) {
@@ -382,13 +382,14 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
       kp.cold_u = reinterpret_cast<uint32_t *>((char *)h->d_cold.ptr + fb);
     }
     h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
-    if (resume || until < std::numeric_limits<double>::infinity()) {
+    if (resume || until < std::numeric_limits<double>::infinity()) {   // == slice
       kp.park_words = 72 + 2 * kp.nf64 + kp.nu32;     // loop-carried registers (<= 72 words) + every shared slot
       CK(h->d_park.reserve((size_t)kp.park_words * kp.n_inst * 4));
       kp.park = h->d_park.as<uint32_t>();
     }
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
-    cudaError_t e = launch_line_kernel(replay, hash, h->sweep, h->want_log, cold, kp, blocks, threads, h->smem_bytes, h->stream);
+    const bool slice = resume || until < std::numeric_limits<double>::infinity();
+    cudaError_t e = launch_line_kernel(replay, hash, slice, h->want_log, cold, kp, blocks, threads, h->smem_bytes, h->stream);
     CK(e);
     launches++;
   }

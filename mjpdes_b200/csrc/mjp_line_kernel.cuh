@@ -112,7 +112,9 @@ __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid, uint64
 // MT == 0: any M, :ends in shared memory.
 // COLD (wide lines): everything that is not read every micro-step lives in an L2-resident scratch
 // [slot][instance] instead of shared memory, so that enough warps fit on an SM.
-template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SWEEP, bool LOG, bool COLD = false>
+// SLICE: the launch may stop at a slice boundary and/or resume parked instances (mjp_launch_slice); kept out
+// of the plain variants because the park/unpark code keeps every state variable alive (4 % on the headline).
+template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SLICE, bool LOG, bool COLD = false>
 __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
   bool active = g < n_inst;
   // A resumed launch continues exactly the instances that were parked at the previous slice boundary.
-  const bool resume = p.resume != 0;
+  const bool resume = SLICE && p.resume != 0;
   if (resume && active && p.status[g] != MJP_INST_PAUSED) active = false;
   const bool fresh_start = active && !resume;
   const bool ran = active;                      // this lane simulates an instance in this launch
@@ -174,11 +176,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     base[(idx >> 2) * stride] = (wd & ~(0xFFu << sh)) | (v << sh);
   };
   // line parameters, with the optional per-instance planes
-  auto lam_of = [&](int i) -> double { return (SWEEP && p.lam_i) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
-  auto mu_of = [&](int i) -> double { return (SWEEP && p.mu_i) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
-  auto cap_of = [&](int b) -> int { return (SWEEP && p.N_i) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
+  auto lam_of = [&](int i) -> double { return (p.lam_i != nullptr) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
+  auto mu_of = [&](int i) -> double { return (p.mu_i != nullptr) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
+  auto cap_of = [&](int b) -> int { return (p.N_i != nullptr) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
   auto dur_of = [&](int k, int i) -> double {
-    if (SWEEP && (p.W_i || p.w_i)) {
+    if (p.W_i || p.w_i) {
       const double wv = p.w_i ? p.w_i[(size_t)(k * M + i) * n_inst + g] : p.w[k * M + i];
       const double Wv = p.W_i ? p.W_i[(size_t)i * n_inst + g] : p.W[i];
       return __ddiv_rn(wv, Wv);
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
       finish(MJP_INST_NORMAL_END); live = false;
     } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
-    else if (clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
+    else if (SLICE && clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -775,7 +777,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   if (!ran) return;
   atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
   n_ev = 0;
-  if (flags & F_PAUSE) {                          // park the untouched state (the lane idled since the boundary)
+  if (SLICE && (flags & F_PAUSE)) {               // park the untouched state (the lane idled since the boundary)
     flags &= ~(uint32_t)F_PAUSE;
     park_save();
     finish(MJP_INST_PAUSED);

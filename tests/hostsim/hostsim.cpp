@@ -20,7 +20,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   kp.N = pl.ci.data(); kp.lvl = pl.ci.data() + (M - 1);
   kp.lam_i = L->lambda_inst; kp.mu_i = L->mu_inst; kp.W_i = L->W_inst; kp.w_i = L->w_inst; kp.N_i = L->N_inst;
   const bool want_log_early = log && L->log;
-  const bool sweep = kp.lam_i || kp.mu_i || kp.W_i || kp.w_i || kp.N_i;
+  const bool sweep = n_slices > 0;     // template slot 5 is SLICE; override planes are a run-time check
   std::vector<double> enters((size_t)kp.R * n_inst);
   kp.enters = enters.data();
   for (size_t q = 0; q < n_inst; ++q) s->status[q] = MJP_INST_NOT_RUN;
