@@ -343,7 +343,7 @@ def main_loop(model: dict, handle=None, out_stream=None, seed: int = DEFAULT_SEE
     from . import engine, scada
     n = model.get(":number-of-simulations") or 1
     if (model.get(":report") or {}).get(":continuous?"):
-        raise ModelError(":continuous? streaming (core.clj:801-849) is not part of the batched run path")
+        return main_loop_continuous(model, handle=handle, seed=seed, mode=mode)          # core.clj:794-795
     start = time.time()
     cl = preprocess_model(model, n_inst=n, seed=seed)
     own = handle is None
@@ -370,3 +370,71 @@ def main_loop(model: dict, handle=None, out_stream=None, seed: int = DEFAULT_SEE
         for r in results:                                                                 # util/log.clj:305-319
             out_stream.write("#_" + scada.pprint_edn({k: v for k, v in r.items() if k != ":jobmix"}) + "\n")
     return results[0] if n == 1 else results
+
+
+# ---- continuous / streaming mode ---------------------------------------------------------------------
+
+class ContinuousModel:
+    """core/main-loop-continuous (core.clj:801-818): a model from which log messages can be pulled
+    indefinitely.  The reference steps the model one micro-step at a time in a go-loop and hands messages
+    over a 30-slot channel; here the device advances the (never-ending) run one time slice at a time with
+    ``mjp_launch_slice`` -- the instance state stays parked in HBM between slices -- and the SCADA records of
+    each slice are queued on the host.  As in the reference, ``:log?`` is forced true and ``:max-lines``
+    infinite (core.clj:812-813), and ``:run-to-time`` does not end the run (one-des-step has no end test).
+    """
+
+    def __init__(self, model: dict, handle=None, seed: int = DEFAULT_SEED, mode: int = abi.RNG_COUNTER,
+                 slice_time: float | None = None, log_capacity: int = 1 << 20):
+        from . import engine
+        m = dict(model)
+        rep = dict(m.get(":report") or {})
+        rep.update({":log?": True, ":max-lines": math.inf})
+        rep.pop(":continuous?", None)
+        m[":report"] = rep
+        self.cl = preprocess_model(m, n_inst=1, seed=seed)
+        self.cl.host.run_to = math.inf                       # never :normal-end
+        self._own = handle is None
+        self.h = handle or engine.Handle(device=0)
+        self.seed, self.mode, self.capacity = seed, mode, int(log_capacity)
+        # a slice should yield a few hundred messages: ~1.4 events per machine per time unit (SURVEY 8d)
+        self.dt = float(slice_time) if slice_time else max(1.0, 400.0 / (1.4 * self.cl.host.M))
+        self.until, self.started, self.queue = 0.0, False, []
+        self.h.upload(self.cl.host, 1)
+        self.h.reserve_log(self.capacity)
+
+    def _advance(self):
+        from . import scada
+        self.until += self.dt
+        self.h.launch_slice(self.until, self.started, mode=self.mode, seed=self.seed, want_log=True)
+        self.h.sync()
+        self.started = True
+        res = self.h.download(log_capacity=self.capacity)
+        if res.rc == abi.LOG_TRUNCATED:                      # slice too long for the buffer: cannot happen silently
+            raise abi.MjpError(res.rc, "SCADA buffer too small for one slice; lower slice_time")
+        st = int(res.stats.status[0])
+        if st != abi.INST_PAUSED:
+            raise abi.MjpError(abi.ERR_INVALID, f"continuous run stopped with status {abi.INST_STATUS_KEYWORD.get(st, st)}")
+        recs = np.sort(res.log, order="line")
+        self.queue.extend(scada.message_map(self.cl, r) for r in recs)
+
+    def pull_data(self, n: int) -> list:
+        """core/pull-data! (core.clj:845-849): the next ``n`` messages."""
+        while len(self.queue) < n:
+            self._advance()
+        out, self.queue = self.queue[:n], self.queue[n:]
+        return out
+
+    def close(self):
+        if self._own and self.h is not None:
+            self.h.close()
+            self.h = None
+
+
+def main_loop_continuous(model: dict, handle=None, seed: int = DEFAULT_SEED, mode: int = abi.RNG_COUNTER,
+                         **kw) -> ContinuousModel:
+    return ContinuousModel(model, handle=handle, seed=seed, mode=mode, **kw)
+
+
+def pull_data(continuous_model: ContinuousModel, n: int) -> list:
+    """(core/pull-data! continuous-model n)"""
+    return continuous_model.pull_data(n)

@@ -213,3 +213,37 @@ def test_main_loop_multi_with_bounds_and_log(engine, oracle):
     want = oracle.run(cl.host, 6, seed=SEED)
     for g, r in enumerate(res):
         assert r[":number-of-jobs"] == int(want.stats.njobs[g])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gid", ["G8", "G9"])
+def test_log_test_clj_through_the_streaming_api(engine, gid):
+    """util/log_test.clj reliable-BAS-pattern / reliable-BBS-pattern, as written there: main-loop on a model with
+    :report {:continuous? true}, (pull-data! model 500), drop the warm-up, partition by 6, compare acts and spans."""
+    g = GOLDENS[gid]
+    cm = model.main_loop(as_model(g["model"]), handle=engine, seed=SEED)
+    assert isinstance(cm, model.ContinuousModel)
+    msgs = model.pull_data(cm, g["pulled"])
+    assert len(msgs) == g["pulled"] and [m[":line"] for m in msgs] == list(range(g["pulled"]))
+    log = [m for m in msgs if m[":clk"] >= g["from_clk"]]
+    groups = [log[i:i + 6] for i in range(0, len(log) - len(log) % 6, 6)]
+    assert len(groups) > 50
+    for grp in groups:
+        assert [m[":act"] for m in grp] == g["cycle"]
+        assert abs((grp[-1][":clk"] - grp[0][":clk"]) - g["span"]) < g["tol"]
+    more = model.pull_data(cm, 1000)                       # keeps going past :run-to-time 100 (core.clj:801-818)
+    assert more[-1][":clk"] > 100.0 and more[0][":line"] == g["pulled"]
+
+
+@pytest.mark.gpu
+def test_streaming_equals_one_shot_capture(engine, oracle):
+    d = dict(GOLDENS["models"]["data/quick.clj"])
+    d[":report"] = {":continuous?": True, ":up&down?": True}
+    cm = model.main_loop(as_model(d), handle=engine, seed=SEED, mode=abi.RNG_REPLAY)
+    msgs = model.pull_data(cm, 3000)
+    cl = cm.cl
+    line = cl.host
+    line.run_to = float(msgs[-1][":clk"]) + 50.0
+    want = oracle.run(line, 1, mode=abi.RNG_REPLAY, seed=SEED, log_capacity=100_000)
+    ref = scada.pull_data(cl, want.log, 3000)
+    assert msgs == ref
