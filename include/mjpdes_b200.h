@@ -52,6 +52,7 @@ enum {
                                  area holds; instance stopped, statistics invalid     */
   MJP_INST_ITER_LIMIT   = 6,  /* device-only: watchdog on loop iterations tripped        */
   MJP_INST_PAUSED       = 7,  /* mjp_launch_slice(): parked at the slice boundary, resumable  */
+  MJP_INST_TAPE_EXHAUSTED = 8, /* MJP_RNG_TAPE: a draw tape ran out                              */
   MJP_INST_NOT_RUN      = 255
 };
 
@@ -125,8 +126,24 @@ typedef struct mjp_line_desc {
  *                     distribution-identical to the loop at core.clj:185-191.
  *   MJP_RNG_REPLAY  : the literal loop of core.clj:185-191, one uniform from
  *                     stream 1+2i, exponentials -ln(u)/rate from stream 2+2i until
- *                     u < 1 - e^(-rate*T); draw counts match the reference's.    */
-enum { MJP_RNG_COUNTER = 0, MJP_RNG_REPLAY = 1 };
+ *                     u < 1 - e^(-rate*T); draw counts match the reference's.
+ *   MJP_RNG_TAPE    : the literal loop again, but every draw is READ from caller-supplied tapes
+ *                     (mjp_set_tapes): the way to replay the reference's OWN stream -- record what
+ *                     clojure.core/rand and incanter's sample-exp returned in a JVM run (with-redefs on
+ *                     the call sites above, one tape per consumer) and feed it here.                 */
+enum { MJP_RNG_COUNTER = 0, MJP_RNG_REPLAY = 1, MJP_RNG_TAPE = 2 };
+
+/* Draw tapes for MJP_RNG_TAPE, instance-major.  `exp` holds the VARIATES sample-exp returned (already
+ * divided by the rate).  An instance that runs off a tape ends with MJP_INST_TAPE_EXHAUSTED.           */
+typedef struct mjp_draw_tapes {
+  uint32_t len_jobtype;     /* draws per instance                                                  */
+  uint32_t len_uniform;     /* draws per machine per instance                                      */
+  uint32_t len_exp;         /* draws per machine per instance                                      */
+  uint32_t reserved;
+  const double *jobtype;    /* [n_inst][len_jobtype]     rand in new-job, core.clj:331              */
+  const double *uniform;    /* [n_inst][M][len_uniform]  rand at core.clj:159 (first), then :185    */
+  const double *exp;        /* [n_inst][M][len_exp]      sample-exp at core.clj:160 (first), :187, :191 */
+} mjp_draw_tapes;
 
 typedef struct mjp_rng_spec {
   int32_t  mode;
@@ -208,6 +225,8 @@ int mjp_run(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst,
 /* Device-resident variant used for measurement: upload once, run many times,
  * download when wanted.  mjp_run() == upload + launch + sync + download.       */
 int mjp_upload(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst);
+/* draw tapes for MJP_RNG_TAPE launches of the uploaded line (copied to the device; call after mjp_upload) */
+int mjp_set_tapes(mjp_handle *h, const mjp_draw_tapes *tapes);
 /* device buffer for SCADA records (needed before a launch with want_log); mjp_run() does it itself */
 int mjp_reserve_log(mjp_handle *h, uint64_t capacity);
 int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log);  /* async on the handle's stream */

@@ -17,7 +17,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, LOG_TRUNCATED = range(6)
 # per-instance status  ([:params :status], core.clj:735,739)
 INST_NORMAL_END, INST_NO_RUNABLES, INST_CLOCK_BACK, INST_JOBTYPE_NIL, INST_LOGBUF_EMPTY, INST_TICK_OVERFLOW = range(6)
-INST_ITER_LIMIT, INST_PAUSED = 6, 7
+INST_ITER_LIMIT, INST_PAUSED, INST_TAPE_EXHAUSTED = 6, 7, 8
 INST_NOT_RUN = 255
 INST_STATUS_KEYWORD = {
     INST_NORMAL_END: ":normal-end",
@@ -28,13 +28,14 @@ INST_STATUS_KEYWORD = {
     INST_TICK_OVERFLOW: ":tick-overflow",
     INST_ITER_LIMIT: ":iteration-limit",
     INST_PAUSED: ":paused",
+    INST_TAPE_EXHAUSTED: ":tape-exhausted",
     INST_NOT_RUN: ":not-run",
 }
 # actions
 ACT_AJ, ACT_UP, ACT_DOWN, ACT_BJ, ACT_EJ, ACT_SM, ACT_ST, ACT_US, ACT_BL, ACT_UB = range(10)
 ACT_KEYWORD = [":aj", ":up", ":down", ":bj", ":ej", ":sm", ":st", ":us", ":bl", ":ub"]
 BAS, BBS = 0, 1
-RNG_COUNTER, RNG_REPLAY = 0, 1
+RNG_COUNTER, RNG_REPLAY, RNG_TAPE = 0, 1, 2
 CFG_EVENT_HASH = 1
 MAX_MACHINES = 64
 MAX_JOBTYPES = 255
@@ -62,6 +63,27 @@ class LineDesc(C.Structure):
 class RngSpec(C.Structure):
     _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64),
                 ("first_instance_id", C.c_uint64)]
+
+
+class DrawTapesStruct(C.Structure):
+    _fields_ = [("len_jobtype", C.c_uint32), ("len_uniform", C.c_uint32), ("len_exp", C.c_uint32),
+                ("reserved", C.c_uint32), ("jobtype", _pd), ("uniform", _pd), ("exp", _pd)]
+
+
+class DrawTapes:
+    """Recorded draws for RNG_TAPE: jobtype [n][Lj], uniform [n][M][Lu], exp [n][M][Le] (f64, instance-major)."""
+
+    def __init__(self, jobtype, uniform, exp):
+        self.jobtype = np.ascontiguousarray(jobtype, np.float64)
+        self.uniform = np.ascontiguousarray(uniform, np.float64)
+        self.exp = np.ascontiguousarray(exp, np.float64)
+        assert self.jobtype.ndim == 2 and self.uniform.ndim == 3 and self.exp.ndim == 3
+
+    def struct(self) -> "DrawTapesStruct":
+        t = DrawTapesStruct()
+        t.len_jobtype, t.len_uniform, t.len_exp = self.jobtype.shape[1], self.uniform.shape[2], self.exp.shape[2]
+        t.jobtype, t.uniform, t.exp = ptr(self.jobtype, C.c_double), ptr(self.uniform, C.c_double), ptr(self.exp, C.c_double)
+        return t
 
 
 class StatsOut(C.Structure):
@@ -241,6 +263,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.mjp_run.argtypes = [H, C.POINTER(LineDesc), C.c_uint64, C.POINTER(RngSpec), C.POINTER(StatsOut),
                             C.POINTER(LogOut)]
     lib.mjp_upload.argtypes = [H, C.POINTER(LineDesc), C.c_uint64]
+    lib.mjp_set_tapes.argtypes = [H, C.POINTER(DrawTapesStruct)]
     lib.mjp_reserve_log.argtypes = [H, C.c_uint64]
     lib.mjp_launch.argtypes = [H, C.POINTER(RngSpec), C.c_int]
     lib.mjp_launch_slice.argtypes = [H, C.POINTER(RngSpec), C.c_int, C.c_double, C.c_int]
@@ -258,6 +281,6 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "mjp_abi_version", "mjp_device_count", "mjp_aggregate_len", "mjp_create", "mjp_destroy", "mjp_last_error",
-    "mjp_run", "mjp_upload", "mjp_reserve_log", "mjp_launch", "mjp_launch_slice", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
+    "mjp_run", "mjp_upload", "mjp_set_tapes", "mjp_reserve_log", "mjp_launch", "mjp_launch_slice", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
     "mjp_last_launch_count", "mjp_probe_end_time",
 ]

@@ -51,7 +51,7 @@ struct mjp_handle {
   mjp::KParams kp{};
   std::vector<int32_t> Ncap;
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage, d_cold, d_park;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage, d_cold, d_park, d_tapes;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -218,7 +218,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_stage, &h->d_cold, &h->d_park})
+                    &h->d_logcur, &h->d_stage, &h->d_cold, &h->d_park, &h->d_tapes})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -333,6 +333,27 @@ int mjp_reserve_log(mjp_handle *h, uint64_t capacity) {
   return MJP_OK;
 }
 
+int mjp_set_tapes(mjp_handle *h, const mjp_draw_tapes *t) {
+  if (!h) return MJP_ERR_INVALID;
+  if (!h->uploaded) return fail(h, MJP_ERR_INVALID, "mjp_set_tapes before mjp_upload");
+  if (!t || !t->jobtype || !t->uniform || !t->exp || !t->len_jobtype || !t->len_uniform || !t->len_exp)
+    return fail(h, MJP_ERR_INVALID, "mjp_draw_tapes: all three tapes are required and must not be empty");
+  CK(cudaSetDevice(h->device));
+  mjp::KParams &kp = h->kp;
+  const size_t n = kp.n_inst, M = kp.M;
+  const size_t bj = align_up(n * t->len_jobtype * 8, 256), bu = align_up(n * M * t->len_uniform * 8, 256),
+               be = n * M * t->len_exp * 8;
+  CK(h->d_tapes.reserve(bj + bu + be));
+  char *base = (char *)h->d_tapes.ptr;
+  CK(cudaMemcpyAsync(base, t->jobtype, n * t->len_jobtype * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(base + bj, t->uniform, n * M * t->len_uniform * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(base + bj + bu, t->exp, be, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  kp.tape_jt = (const double *)base; kp.tape_u = (const double *)(base + bj); kp.tape_e = (const double *)(base + bj + bu);
+  kp.tape_len_jt = t->len_jobtype; kp.tape_len_u = t->len_uniform; kp.tape_len_e = t->len_exp;
+  return MJP_OK;
+}
+
 int mjp_launch(mjp_handle *h, const mjp_rng_spec *rng, int want_log) {
   return mjp_launch_slice(h, rng, want_log, std::numeric_limits<double>::infinity(), 0);
 }
@@ -342,8 +363,10 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
   if (!h->uploaded) return fail(h, MJP_ERR_INVALID, "mjp_launch before mjp_upload");
   if (resume && !h->launched) return fail(h, MJP_ERR_INVALID, "resume without a previous sliced launch");
   if (!(until == until)) return fail(h, MJP_ERR_INVALID, "slice boundary is NaN");
-  if (!rng || (rng->mode != MJP_RNG_COUNTER && rng->mode != MJP_RNG_REPLAY))
+  if (!rng || rng->mode < MJP_RNG_COUNTER || rng->mode > MJP_RNG_TAPE)
     return fail(h, MJP_ERR_INVALID, "bad mjp_rng_spec");
+  if (rng->mode == MJP_RNG_TAPE && !h->kp.tape_u)
+    return fail(h, MJP_ERR_INVALID, "MJP_RNG_TAPE: call mjp_set_tapes after mjp_upload first");
   CK(cudaSetDevice(h->device));
   mjp::KParams &kp = h->kp;
   kp.seed = rng->seed;
@@ -358,7 +381,7 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
   }
   CK(cudaMemsetAsync(h->d_logcur.ptr, 0, 16, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
-  const bool replay = rng->mode == MJP_RNG_REPLAY, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
+  const bool replay = rng->mode != MJP_RNG_COUNTER, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
   if (h->want_log && !kp.log_records) return fail(h, MJP_ERR_INVALID, "SCADA capture wanted: call mjp_reserve_log first");
   {
     int threads = h->block_threads;
@@ -389,7 +412,9 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     }
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
     const bool slice = resume || until < std::numeric_limits<double>::infinity();
-    cudaError_t e = launch_line_kernel(replay, hash, slice, h->want_log, cold, kp, blocks, threads, h->smem_bytes, h->stream);
+    mjp::KParams kl = kp;                         // tapes are read by MJP_RNG_TAPE launches only
+    if (rng->mode != MJP_RNG_TAPE) kl.tape_jt = kl.tape_u = kl.tape_e = nullptr;
+    cudaError_t e = launch_line_kernel(replay, hash, slice, h->want_log, cold, kl, blocks, threads, h->smem_bytes, h->stream);
     CK(e);
     launches++;
   }

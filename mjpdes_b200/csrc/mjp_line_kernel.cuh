@@ -80,18 +80,31 @@ __device__ MJP_NOINLINE double sojourn_counter(uint32_t idx, uint32_t consumer, 
   philox4x32_10(idx, consumer, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
   return __ddiv_rn(-det_log(__dmul_rn(u52open(o[0], o[1]), u52open(o[2], o[3]))), rate);
 }
-// sojourn of REPLAY mode: the literal loop of core.clj:185-191; e is the cursor of the exponential stream
+// sojourn of REPLAY / TAPE mode: the literal loop of core.clj:185-191; e is the cursor of the exponential
+// stream.  tu/te != nullptr: the draws are read from this machine's tapes (NaN once a tape is exhausted).
 __device__ MJP_NOINLINE double sojourn_replay(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate,
-                                             uint32_t *e_io) {
+                                             uint32_t *e_io, const double *tu, const double *te, uint32_t len_u,
+                                             uint32_t len_e) {
   uint32_t o[4], e = *e_io;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), g0 = (uint32_t)gid, g1 = (uint32_t)(gid >> 32);
-  philox4x32_10(idx, consumer, g0, g1, k0, k1, o);
-  const double some_num = u53(o[0], o[1]);                                     // core.clj:185
-  philox4x32_10(e++, consumer + 1u, g0, g1, k0, k1, o);
-  double T = __ddiv_rn(-det_log(u52open(o[0], o[1])), rate);                   // core.clj:187
-  while (!(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {        // core.clj:188, 162-165
+  const double QN = __longlong_as_double(0x7FF8000000000000ll);
+  double some_num, T;
+  if (tu) {
+    some_num = idx < len_u ? tu[idx] : QN;                                     // core.clj:185
+    T = e < len_e ? te[e] : QN; ++e;                                           // core.clj:187
+    while (T == T && some_num == some_num && !(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {
+      T = __dadd_rn(T, e < len_e ? te[e] : QN); ++e;                           // core.clj:190-191
+    }
+    if (!(some_num == some_num)) T = QN;
+  } else {
+    philox4x32_10(idx, consumer, g0, g1, k0, k1, o);
+    some_num = u53(o[0], o[1]);                                                // core.clj:185
     philox4x32_10(e++, consumer + 1u, g0, g1, k0, k1, o);
-    T = __dadd_rn(T, __ddiv_rn(-det_log(u52open(o[0], o[1])), rate));          // core.clj:190-191
+    T = __ddiv_rn(-det_log(u52open(o[0], o[1])), rate);                        // core.clj:187
+    while (!(some_num < __dadd_rn(1.0, -det_exp(-__dmul_rn(rate, T))))) {      // core.clj:188, 162-165
+      philox4x32_10(e++, consumer + 1u, g0, g1, k0, k1, o);
+      T = __dadd_rn(T, __ddiv_rn(-det_log(u52open(o[0], o[1])), rate));        // core.clj:190-191
+    }
   }
   *e_io = e;
   return T;
@@ -220,9 +233,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   auto next_event_time = [&](int i, uint32_t n_prev, bool prev_is_up, double t_prev, uint32_t &e) -> double {
     const double rate = prev_is_up ? lam_of(i) : mu_of(i);
     const uint64_t gid = p.first_id + g;
-    const double T = REPLAY ? sojourn_replay(n_prev + 1, 1u + 2u * i, gid, p.seed, rate, &e)
+    const bool tape = REPLAY && p.tape_u != nullptr;
+    const double T = REPLAY ? sojourn_replay(n_prev + 1, 1u + 2u * i, gid, p.seed, rate, &e,
+                                             tape ? p.tape_u + ((size_t)g * M + i) * p.tape_len_u : nullptr,
+                                             tape ? p.tape_e + ((size_t)g * M + i) * p.tape_len_e : nullptr,
+                                             p.tape_len_u, p.tape_len_e)
                             : sojourn_counter(n_prev + 1, 1u + 2u * i, gid, p.seed, rate);
-    return __dadd_rn(t_prev, T);
+    return __dadd_rn(t_prev, T);                      // NaN when a tape ran out: caught at the use sites
   };
 
   // ---- preprocess-model: first up/down event of each machine (core.clj:156-160,557-562) ----
@@ -231,18 +248,29 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const double lam = lam_of(i), mu = mu_of(i);
     const double p_up = __ddiv_rn(mu, __dadd_rn(lam, mu));
     uint32_t o[4];
-    px(0u, 1u + 2u * i, o);
-    const bool is_up = u53(o[0], o[1]) < p_up;
-    double eu;
-    if (REPLAY) {
-      uint32_t o2[4];
-      px(0u, 2u + 2u * i, o2);
-      eu = u52open(o2[0], o2[1]);
+    bool is_up;
+    double first;                                   // sample-exp 1 :rate (if up? lambda mu), core.clj:160
+    if (REPLAY && p.tape_u != nullptr) {
+      const double u0 = p.tape_len_u ? p.tape_u[((size_t)g * M + i) * p.tape_len_u] : QNAN;
+      first = p.tape_len_e ? p.tape_e[((size_t)g * M + i) * p.tape_len_e] : QNAN;
+      if (!(u0 == u0)) first = QNAN;
+      is_up = u0 < p_up;
       s_eidx[i * cs] = 1u;
     } else {
-      eu = u52open(o[2], o[3]);
+      px(0u, 1u + 2u * i, o);
+      is_up = u53(o[0], o[1]) < p_up;
+      double eu;
+      if (REPLAY) {
+        uint32_t o2[4];
+        px(0u, 2u + 2u * i, o2);
+        eu = u52open(o2[0], o2[1]);
+        s_eidx[i * cs] = 1u;
+      } else {
+        eu = u52open(o[2], o[3]);
+      }
+      first = __ddiv_rn(-det_log(eu), is_up ? lam : mu);
     }
-    FUT_T(i) = __ddiv_rn(-det_log(eu), is_up ? lam : mu);
+    FUT_T(i) = first;
     FUT_N(i) = 0u;
     STARTED(i) = 0u;
     set_end(i, 0.0);
@@ -284,9 +312,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // steady accumulators kept in registers
   // tick / loop flags share one register: F_EJ this tick has an :ej, F_TICK TICKCLK == clock,
   // F_OVF a per-tick structure overflowed
-  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8 };   // F_PAUSE: stopped at a slice boundary
+  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8, F_TAPE = 16 };   // F_PAUSE: stopped at a slice boundary; F_TAPE: a draw tape ran out
   uint32_t flags = 0;
   auto finish = [&](int code) { p.status[g] = (uint8_t)code; };     // the instance ends with this :status
+  if (REPLAY && fresh_start)
+    for (int i = 0; i < M; ++i) if (!(FUT_T(i) == FUT_T(i))) flags |= F_TAPE;   // a tape too short for the first event
 
   int type_cache = -2;                 // job type of the NEXT job when already drawn (-2: not drawn)
 
@@ -607,13 +637,18 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         if (K == 1 && c_thr[0] >= 1.0) type = 0;
         else if (type_cache != -2) { type = type_cache; type_cache = -2; }
         else {
-          double u0, u1;
-          jobtype_uniforms(curjob >> 1, p.first_id + g, p.seed, &u0, &u1);
-          if (curjob & 1) type = type_from(u1);
-          else { type = type_from(u0); type_cache = type_from(u1); }
+          if (REPLAY && p.tape_jt != nullptr) {             // MJP_RNG_TAPE: rand of new-job, core.clj:331
+            if (curjob < p.tape_len_jt) type = type_from(p.tape_jt[(size_t)g * p.tape_len_jt + curjob]);
+            else { type = -1; flags |= F_TAPE; }
+          } else {
+            double u0, u1;
+            jobtype_uniforms(curjob >> 1, p.first_id + g, p.seed, &u0, &u1);
+            if (curjob & 1) type = type_from(u1);
+            else { type = type_from(u0); type_cache = type_from(u1); }
+          }
         }
         if (type < 0) {                                      // the reference dies in job-requires
-          finish(MJP_INST_JOBTYPE_NIL); live = false;
+          finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED : MJP_INST_JOBTYPE_NIL); live = false;
           b_ud = b_tb = b_tm = b_st = b_us = b_bl = b_ub = 0;
         } else {
           const uint32_t id = curjob + 1;
@@ -639,6 +674,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
               if (up & 1) t = after(false, t);                 // the :up after the pending :down
               for (;;) {
                 const double t_dn = after(true, t);
+                if (!(t_dn == t_dn)) { v = QNAN; flags |= F_TAPE; break; }       // tape exhausted
                 if (!end_time_resume(t, t_dn, rem, v)) break;
                 rem = v;
                 t = after(false, t_dn);
@@ -679,6 +715,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
             t_next = next_event_time(i, n, was_up_event, t_fire, ecur);
             if (REPLAY) s_eidx[i * cs] = ecur;
           } else t_next = NXT_T(i);
+          if (REPLAY && !(t_next == t_next)) flags |= F_TAPE;
           need |= bit;
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
           if (was_up_event && (pend & bit)) {                // end-time resumes at this :up  core.clj:145-151
@@ -769,7 +806,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         else { B ^= bit; toggle(pB, twoB, bit); }
       }
     }
-    if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW); live = false; }
+    if (live && (flags & F_TAPE)) { finish(MJP_INST_TAPE_EXHAUSTED); live = false; }
+    else if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW); live = false; }
     else if (live && seen == 0) { finish(MJP_INST_LOGBUF_EMPTY); live = false; }    // push-log returned nil, util/log.clj:95
     active = live;
     }

@@ -37,6 +37,9 @@ struct KParams {
   int32_t resume;         // 1: continue the instances parked by the previous launch
   int32_t park_words;     // rows of `park`
   uint32_t *park;         // [park_words][n_inst] parked per-instance state
+  // MJP_RNG_TAPE: recorded draws, instance-major (nullptr: draw from the Philox substreams)
+  const double *tape_jt, *tape_u, *tape_e;
+  uint32_t tape_len_jt, tape_len_u, tape_len_e, tape_pad;
   // SCADA records
   void *log_records;      // mjp_log_record[log_capacity]
   uint64_t log_capacity;

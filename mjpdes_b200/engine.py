@@ -92,6 +92,21 @@ class Handle:
         self._check(self._lib.mjp_upload(self._h, C.byref(desc), int(n_inst)))
         self._line, self._n = line, int(n_inst)
 
+    def set_tapes(self, tapes: abi.DrawTapes):
+        """Recorded draws for ``mode=abi.RNG_TAPE`` launches of the uploaded line."""
+        t = tapes.struct()
+        self._check(self._lib.mjp_set_tapes(self._h, C.byref(t)))
+
+    def run_tape(self, line: abi.HostLine, n_inst: int, tapes: abi.DrawTapes, log_capacity: int = 0) -> "RunResult":
+        """``run`` with every draw read from ``tapes`` (the reference's own stream, recorded in a JVM run)."""
+        self.upload(line, n_inst)
+        self.set_tapes(tapes)
+        if log_capacity:
+            self.reserve_log(log_capacity)
+        self.launch(abi.RNG_TAPE, 0, 0, want_log=bool(log_capacity))
+        self.sync()
+        return self.download(log_capacity=log_capacity)
+
     def reserve_log(self, capacity: int):
         """Device buffer for SCADA records; needed before ``launch(want_log=True)``."""
         self._check(self._lib.mjp_reserve_log(self._h, int(capacity)))

@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         pd, pu8 = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
         l.mjpo_run.argtypes = [C.POINTER(abi.LineDesc), C.c_uint64, C.POINTER(abi.RngSpec),
                                C.POINTER(abi.StatsOut), C.POINTER(abi.LogOut), C.POINTER(Extra), C.c_int]
+        l.mjpo_set_tapes.argtypes = [C.POINTER(abi.DrawTapesStruct)]
+        l.mjpo_set_tapes.restype = None
         l.mjpo_end_time.argtypes = [pu8, pd, C.c_int32, C.c_double, C.c_double]
         l.mjpo_end_time.restype = C.c_double
         l.mjpo_updown_events.argtypes = [C.c_double, C.c_double, C.POINTER(abi.RngSpec), C.c_uint64, C.c_int32,
@@ -79,7 +81,7 @@ class OracleResult:
 
 
 def run(line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int = 0, first_instance_id: int = 0,
-        log_capacity: int = 0, n_threads: int = 1) -> OracleResult:
+        log_capacity: int = 0, n_threads: int = 1, tapes: abi.DrawTapes | None = None) -> OracleResult:
     """main-loop-loop (core.clj:729-744) for ``n_inst`` instances on the CPU."""
     l = lib()
     n = int(n_inst)
@@ -94,11 +96,30 @@ def run(line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int 
               abi.ptr(ex["ticks"], C.c_uint64), abi.ptr(ex["max_tick_msgs"], C.c_uint32),
               abi.ptr(ex["max_lookahead"], C.c_uint32))
     s = stats.struct()
+    ts = tapes.struct() if tapes is not None else None
+    l.mjpo_set_tapes(C.byref(ts) if ts is not None else None)
     rc = l.mjpo_run(C.byref(desc), n, C.byref(rng), C.byref(s),
                     C.byref(hlog.struct()) if hlog else None, C.byref(e), int(n_threads))
+    l.mjpo_set_tapes(None)
     if rc not in (abi.OK, abi.LOG_TRUNCATED):
         raise abi.MjpError(rc, "oracle rejected the descriptor")
     return OracleResult(stats, hlog.view().copy() if hlog else None, ex, rc)
+
+
+def record_tapes(line: abi.HostLine, n_inst: int, seed: int, len_jobtype: int, len_uniform: int, len_exp: int,
+                 first_instance_id: int = 0):
+    """Run REPLAY and record every draw per consumer: what hooking rand / sample-exp in a JVM run would give."""
+    l = lib()
+    l.mjpo_record_tapes.argtypes = [C.POINTER(abi.LineDesc), C.c_uint64, C.POINTER(abi.RngSpec),
+                                    C.POINTER(abi.DrawTapesStruct), C.POINTER(C.c_uint32)]
+    n, M = int(n_inst), line.M
+    tapes = abi.DrawTapes(np.full((n, len_jobtype), np.nan), np.full((n, M, len_uniform), np.nan),
+                          np.full((n, M, len_exp), np.nan))
+    used = np.zeros((n, 2 * M + 1), np.uint32)
+    d, r, t = line.desc(), abi.RngSpec(abi.RNG_REPLAY, 0, seed, first_instance_id), tapes.struct()
+    rc = l.mjpo_record_tapes(C.byref(d), n, C.byref(r), C.byref(t), abi.ptr(used, C.c_uint32))
+    assert rc == 0, rc
+    return tapes, used
 
 
 def end_time(kinds, times, clock: float, dur: float) -> float:

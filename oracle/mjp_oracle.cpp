@@ -150,19 +150,35 @@ struct UpDown {
   bool finite = false;          /* literal seq, or '([0 :down ##Inf]) for lambda == 0 */
   std::vector<Ev> seq;          /* realised prefix; the head is retained, as in the reference */
   uint32_t u_idx = 0, e_idx = 0;
+  /* MJP_RNG_TAPE: recorded draws of this machine (what rand / sample-exp returned in a JVM run) */
+  const double *tape_u = nullptr, *tape_e = nullptr;
+  uint32_t len_u = 0, len_e = 0;
+  bool exhausted = false;
+  /* recording (what a JVM user does with with-redefs on rand / sample-exp): every draw as returned */
+  double *rec_u = nullptr, *rec_e = nullptr; uint32_t rec_len_u = 0, rec_len_e = 0, rec_nu = 0, rec_ne = 0;
+  double note_u(double v) { if (rec_u && rec_nu < rec_len_u) rec_u[rec_nu] = v; ++rec_nu; return v; }
+  double note_e(double v) { if (rec_e && rec_ne < rec_len_e) rec_e[rec_ne] = v; ++rec_ne; return v; }
+  double tape_uniform() { if (u_idx < len_u) return tape_u[u_idx++]; exhausted = true; ++u_idx; return kNaN; }
+  double tape_exp() { if (e_idx < len_e) return tape_e[e_idx++]; exhausted = true; ++e_idx; return kNaN; }
 
   uint32_t cu() const { return 1u + 2u * (uint32_t)mach; }
   uint32_t ce() const { return 2u + 2u * (uint32_t)mach; }
 
   /* sample-exp 1 :rate r  ==  -ln(U)/r  (incanter -> Colt Exponential) */
-  double exp_draw(double rate) { return -det_log(d->open_uniform(ce(), e_idx++)) / rate; }
+  double exp_draw(double rate) { return note_e(-det_log(d->open_uniform(ce(), e_idx++)) / rate); }
 
   /* expo-up&down-init-event core:156-160, then expo-up&down core:174-179 */
   void init() {
     double u, e;
     double p_up = mu / (lambda + mu);
-    if (mode == MJP_RNG_REPLAY) {
-      u = d->uniform(cu(), u_idx++);
+    if (mode == MJP_RNG_TAPE) {
+      u = tape_uniform();
+      bool up = u < p_up;
+      e = tape_exp();
+      if (exhausted) e = kNaN;
+      seq.push_back({0, (uint8_t)(up ? EV_DOWN : EV_UP), e});
+    } else if (mode == MJP_RNG_REPLAY) {
+      u = note_u(d->uniform(cu(), u_idx++));
       bool up = u < p_up;
       e = exp_draw(up ? lambda : mu);
       seq.push_back({0, (uint8_t)(up ? EV_DOWN : EV_UP), e});
@@ -182,8 +198,14 @@ struct UpDown {
     bool up_now = (prev.kind == EV_UP);
     double rate = up_now ? lambda : mu;
     double T;
-    if (mode == MJP_RNG_REPLAY) {
-      double some_num = d->uniform(cu(), u_idx++);                 /* core:185 */
+    if (mode == MJP_RNG_TAPE) {
+      double some_num = tape_uniform();                            /* core:185 */
+      T = tape_exp();                                              /* core:187 */
+      while (!exhausted && !(some_num < 1.0 - det_exp(-(rate * T))))
+        T = T + tape_exp();                                        /* core:190-191 */
+      if (exhausted) T = kNaN;
+    } else if (mode == MJP_RNG_REPLAY) {
+      double some_num = note_u(d->uniform(cu(), u_idx++));         /* core:185 */
       T = exp_draw(rate);                                          /* core:187 */
       while (!(some_num < 1.0 - det_exp(-(rate * T))))             /* core:188, p-state-change core:162-165 */
         T = T + exp_draw(rate);                                    /* core:190-191 */
@@ -198,7 +220,7 @@ struct UpDown {
   /* (nth up&down k), nullptr past the end of a finite seq */
   const Ev *at(size_t k) {
     while (seq.size() <= k) {
-      if (finite) return nullptr;
+      if (finite || exhausted) return nullptr;     /* a dry tape ends the seq; the loop reports it */
       realise_next();
     }
     return &seq[k];
@@ -250,6 +272,8 @@ struct Sim {
   Steady steady;
   Draws draws;
   uint32_t jt_idx = 0;
+  const double *tape_jt = nullptr; uint32_t len_jt = 0; bool tape_out = false;
+  double *rec_jt = nullptr; uint32_t rec_len_jt = 0;
   int status = MJP_INST_NOT_RUN;
   /* instrumentation */
   uint64_t n_events = 0, hash = 0xcbf29ce484222325ull, iterations = 0, ticks = 0;
@@ -376,8 +400,14 @@ struct Sim {
   Job new_job() {
     /* draw #d of consumer 0 is half (d & 1) of Philox block {d >> 1, 0} (include/mjpdes_b200.h) */
     uint32_t d = jt_idx++, o[4];
-    draws.block(0, d >> 1, o);
-    double choose = (d & 1) ? Draws::u53(o[2], o[3]) : Draws::u53(o[0], o[1]);
+    double choose;
+    if (tape_jt) {
+      if (d < len_jt) choose = tape_jt[d]; else { choose = kNaN; tape_out = true; }
+    } else {
+      draws.block(0, d >> 1, o);
+      choose = (d & 1) ? Draws::u53(o[2], o[3]) : Draws::u53(o[0], o[1]);
+      if (rec_jt && d < rec_len_jt) rec_jt[d] = choose;
+    }
     int type = -1;
     double accum = portion[0];
     for (int k = 0; k < K; ++k) {
@@ -551,11 +581,14 @@ struct Sim {
       double next_clk = acts[0].time;
       if (next_clk == kInf) { status = MJP_INST_NO_RUNABLES; return; }      /* D2 */
       if (clock > next_clk) { status = MJP_INST_CLOCK_BACK; return; }       /* advance-clock core:128-135 */
-      for (const Act &a : acts) if (a.fn == FN_AJ && a.job.type < 0) { status = MJP_INST_JOBTYPE_NIL; return; }
+      for (const Act &a : acts) if (a.fn == FN_AJ && a.job.type < 0) {
+        status = tape_out ? MJP_INST_TAPE_EXHAUSTED : MJP_INST_JOBTYPE_NIL; return;
+      }
       clock = next_clk;
       iterations++;
       if (clock != last_clock) { ticks++; last_clock = clock; }
       for (const Act &a : acts) run_action(a);                              /* core:742 */
+      for (const Machine &mc : mach) if (mc.ud.exhausted) { status = MJP_INST_TAPE_EXHAUSTED; return; }
       if (!push_log()) { status = MJP_INST_LOGBUF_EMPTY; return; }          /* core:743 */
     }
   }
@@ -580,6 +613,8 @@ bool valid_desc(const mjp_line_desc *L, uint64_t n_inst) {
 }
 
 /* preprocess-model core:578-615 restricted to what the loop reads */
+const mjp_draw_tapes *g_tapes = nullptr;      /* set by mjpo_set_tapes for MJP_RNG_TAPE runs */
+
 void build_sim(Sim &s, const mjp_line_desc *L, uint64_t n_inst, uint64_t g, const mjp_rng_spec *rng) {
   s.M = L->M; s.K = L->K;
   s.draws.seed = rng->seed; s.draws.inst = rng->first_instance_id + g;
@@ -589,6 +624,9 @@ void build_sim(Sim &s, const mjp_line_desc *L, uint64_t n_inst, uint64_t g, cons
   s.w.resize((size_t)s.K * s.M);
   for (int q = 0; q < s.K * s.M; ++q) s.w[q] = L->w_inst ? L->w_inst[(size_t)q * n_inst + g] : L->w[q];
   for (int b = 0; b < s.M - 1; ++b) s.N[b] = L->N_inst ? L->N_inst[(size_t)b * n_inst + g] : L->N[b];
+  if (rng->mode == MJP_RNG_TAPE && g_tapes) {
+    s.tape_jt = g_tapes->jobtype + (size_t)g * g_tapes->len_jobtype; s.len_jt = g_tapes->len_jobtype;
+  }
   s.clock = 0.0; s.warm_up = L->warm_up; s.run_to = L->run_to; s.run_to_job = L->run_to_job;
   s.jm2dm = L->jm2dm; s.log_on = L->log; s.up_down = L->up_down; s.max_lines = L->max_lines;
   for (int i = 0; i < s.M; ++i) {
@@ -598,6 +636,10 @@ void build_sim(Sim &s, const mjp_line_desc *L, uint64_t n_inst, uint64_t g, cons
     m.ud.lambda = L->lambda_inst ? L->lambda_inst[(size_t)i * n_inst + g] : L->lambda[i];
     m.ud.mu = L->mu_inst ? L->mu_inst[(size_t)i * n_inst + g] : L->mu[i];
     m.ud.mach = i; m.ud.mode = rng->mode; m.ud.d = &s.draws;
+    if (rng->mode == MJP_RNG_TAPE && g_tapes) {
+      m.ud.tape_u = g_tapes->uniform + ((size_t)g * s.M + i) * g_tapes->len_uniform; m.ud.len_u = g_tapes->len_uniform;
+      m.ud.tape_e = g_tapes->exp + ((size_t)g * s.M + i) * g_tapes->len_exp; m.ud.len_e = g_tapes->len_exp;
+    }
     m.ud.init();                              /* preprocess-equip core:557-562 */
     m.future = m.ud.seq[0];
   }
@@ -639,9 +681,42 @@ extern "C" {
 
 int mjp_aggregate_len_oracle(int32_t M) { return 1 + 2 * (3 * M + 1); }
 
+void mjpo_set_tapes(const mjp_draw_tapes *t) { g_tapes = t; }
+
+/* Run in MJP_RNG_REPLAY and RECORD every draw per consumer into caller buffers shaped like mjp_draw_tapes
+ * (the buffers behind the const pointers are written).  used[g*(2M+1) + ...] = draws consumed:
+ * [0] job type, [1+i] uniforms of machine i, [1+M+i] exponentials of machine i.                        */
+int mjpo_record_tapes(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, const mjp_draw_tapes *out,
+                      uint32_t *used) {
+  if (!rng || rng->mode != MJP_RNG_REPLAY || !valid_desc(L, n_inst) || L->M < 2 || !out) return MJP_ERR_INVALID;
+  const int M = L->M;
+  for (uint64_t g = 0; g < n_inst; ++g) {
+    Sim s;
+    build_sim(s, L, n_inst, g, rng);
+    /* build_sim already drew the first event of every machine: replay those two draws into the tapes */
+    s.rec_jt = const_cast<double *>(out->jobtype) + (size_t)g * out->len_jobtype; s.rec_len_jt = out->len_jobtype;
+    for (int i = 0; i < M; ++i) {
+      UpDown &u = s.mach[i].ud;
+      u.rec_u = const_cast<double *>(out->uniform) + ((size_t)g * M + i) * out->len_uniform; u.rec_len_u = out->len_uniform;
+      u.rec_e = const_cast<double *>(out->exp) + ((size_t)g * M + i) * out->len_exp; u.rec_len_e = out->len_exp;
+      u.rec_nu = u.rec_ne = 0;
+      u.note_u(s.draws.uniform(u.cu(), 0));
+      u.note_e(u.seq[0].t);
+    }
+    s.main_loop_loop();
+    if (used) {
+      uint32_t *row = used + (size_t)g * (2 * M + 1);
+      row[0] = s.jt_idx;
+      for (int i = 0; i < M; ++i) { row[1 + i] = s.mach[i].ud.rec_nu; row[1 + M + i] = s.mach[i].ud.rec_ne; }
+    }
+  }
+  return MJP_OK;
+}
+
 int mjpo_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng,
              mjp_stats_out *stats, mjp_log_out *log, mjpo_extra *extra, int n_threads) {
   if (!rng || !valid_desc(L, n_inst) || L->M < 2) return MJP_ERR_INVALID;
+  if (rng->mode == MJP_RNG_TAPE && !g_tapes) return MJP_ERR_INVALID;
   if (n_threads < 1) n_threads = 1;
   if ((uint64_t)n_threads > n_inst) n_threads = (int)(n_inst ? n_inst : 1);
   std::vector<std::vector<mjp_log_record>> sinks(n_inst && log && log->records ? n_inst : 0);

@@ -40,6 +40,13 @@ typedef struct mjpo_extra {
 int mjpo_run(const mjp_line_desc *line, uint64_t n_inst, const mjp_rng_spec *rng,
              mjp_stats_out *stats, mjp_log_out *log, mjpo_extra *extra, int n_threads);
 
+/* tapes for subsequent MJP_RNG_TAPE runs (pointer kept, not copied; NULL clears) */
+void mjpo_set_tapes(const mjp_draw_tapes *tapes);
+
+/* record the draws of a MJP_RNG_REPLAY run per consumer (stand-in for hooking rand / sample-exp in a JVM) */
+int mjpo_record_tapes(const mjp_line_desc *line, uint64_t n_inst, const mjp_rng_spec *rng,
+                      const mjp_draw_tapes *out, uint32_t *used);
+
 /* end-time (core.clj:138-151) over a literal :up&down seq (core_test.clj:26-45). */
 double mjpo_end_time(const uint8_t *kinds, const double *times, int32_t n_events,
                      double clock, double dur);

@@ -41,7 +41,7 @@ static int run_case(int M, int K, int n, double run_to, int mode, bool log, bool
     mjp::LinePlan pl = mjp::build_plan(&L, n);
     mjp::KParams kp = pl.kp;
     const bool mt = !cold && !log && M <= 8;
-    const size_t used = kp.const_bytes + mjp::plan_layout(kp, mt, mode == MJP_RNG_REPLAY, log, cold);
+    const size_t used = kp.const_bytes + mjp::plan_layout(kp, mt, mode != MJP_RNG_COUNTER, log, cold);
     ASAN_UNPOISON_MEMORY_REGION(mjp::smem_raw, sizeof(mjp::smem_raw));
     ASAN_POISON_MEMORY_REGION(mjp::smem_raw + used, sizeof(mjp::smem_raw) - used);
   }

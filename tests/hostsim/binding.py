@@ -35,21 +35,22 @@ def lib():
                                      C.POINTER(abi.StatsOut), C.c_int, C.POINTER(abi.LogOut), C.c_int]
         _LIB.hostsim_run_sliced.argtypes = [C.POINTER(abi.LineDesc), C.c_uint64, C.POINTER(abi.RngSpec),
                                             C.POINTER(abi.StatsOut), C.c_int, C.POINTER(abi.LogOut), C.c_int,
-                                            C.POINTER(C.c_double), C.c_int]
+                                            C.POINTER(C.c_double), C.c_int, C.POINTER(abi.DrawTapesStruct)]
         _LIB.hostsim_end_time.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double]
         _LIB.hostsim_end_time.restype = C.c_double
     return _LIB
 
 
 def run(line, n_inst, mode=abi.RNG_COUNTER, seed=0, first_instance_id=0, want_hash=True, log_capacity=0, cold=False,
-        slices=()):
+        slices=(), tapes=None):
     stats = abi.HostStats(line, n_inst)
     d, r, s = line.desc(), abi.RngSpec(mode, 0, seed, first_instance_id), stats.struct()
     hlog = abi.HostLog(log_capacity) if log_capacity else None
     sl = np.ascontiguousarray(slices, np.float64)
     rc = lib().hostsim_run_sliced(C.byref(d), n_inst, C.byref(r), C.byref(s), int(want_hash),
                                   C.byref(hlog.struct()) if hlog else None, int(cold),
-                                  abi.ptr(sl, C.c_double) if len(sl) else None, len(sl))
+                                  abi.ptr(sl, C.c_double) if len(sl) else None, len(sl),
+                                  C.byref(tapes.struct()) if tapes is not None else None)
     assert rc == 0, rc
     if hlog:
         stats.log = hlog.view().copy()

@@ -9,11 +9,16 @@
 
 // One launch per slice boundary in `slices` (then one to the end), resuming the parked state each time.
 extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
-                                  int want_hash, mjp_log_out *log, int force_cold, const double *slices, int n_slices) {
+                                  int want_hash, mjp_log_out *log, int force_cold, const double *slices, int n_slices,
+                                  const mjp_draw_tapes *tapes) {
   mjp::LinePlan pl = mjp::build_plan(L, n_inst);
   mjp::KParams kp = pl.kp;
   const int M = kp.M;
   kp.seed = rng->seed; kp.first_id = rng->first_instance_id;
+  if (rng->mode == MJP_RNG_TAPE && tapes) {
+    kp.tape_jt = tapes->jobtype; kp.tape_u = tapes->uniform; kp.tape_e = tapes->exp;
+    kp.tape_len_jt = tapes->len_jobtype; kp.tape_len_u = tapes->len_uniform; kp.tape_len_e = tapes->len_exp;
+  }
   const double *dc = pl.cd.data();
   kp.lam = dc + pl.off_lam(); kp.mu = dc + pl.off_mu(); kp.W = dc + pl.off_W(); kp.w = dc + pl.off_w();
   kp.dur = dc + pl.off_dur(); kp.thr = dc + pl.off_thr();
@@ -29,7 +34,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; s->n_events[q] = 0; }
   const bool cold = force_cold != 0;
   const bool mt_ok = !cold && !want_log_early && M >= 2 && M <= 8;
-  mjp::plan_layout(kp, mt_ok, rng->mode == MJP_RNG_REPLAY, want_log_early, cold);
+  mjp::plan_layout(kp, mt_ok, rng->mode != MJP_RNG_COUNTER, want_log_early, cold);
   std::vector<double> coldf((size_t)mjp::cold_f64_slots(kp) * n_inst);
   std::vector<uint32_t> coldu((size_t)mjp::cold_u32_slots(kp, true) * n_inst);
   kp.cold_f = coldf.data(); kp.cold_u = coldu.data();
@@ -37,7 +42,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   kp.occ = s->occ_time; kp.final_clock = s->final_clock; kp.curjob = s->current_job; kp.n_events = s->n_events;
   kp.hash = s->event_hash; kp.status = s->status;
   if (pl.kp.const_bytes + pl.per_thread_bytes > sizeof(mjp::smem_raw)) return MJP_ERR_UNSUPPORTED;
-  const bool replay = rng->mode == MJP_RNG_REPLAY, hash = want_hash != 0;
+  const bool replay = rng->mode != MJP_RNG_COUNTER, hash = want_hash != 0;
   unsigned long long cursor[2] = {0, 0};
   const bool want_log = log && L->log;
   if (want_log) { kp.log_records = log->records; kp.log_capacity = log->capacity; kp.log_cursor = cursor; }
@@ -103,7 +108,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
 
 extern "C" int hostsim_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
                            int want_hash, mjp_log_out *log, int force_cold) {
-  return hostsim_run_sliced(L, n_inst, rng, s, want_hash, log, force_cold, nullptr, 0);
+  return hostsim_run_sliced(L, n_inst, rng, s, want_hash, log, force_cold, nullptr, 0, nullptr);
 }
 
 extern "C" double hostsim_end_time(const uint8_t *kinds, const double *times, int n, double clock, double dur) {
