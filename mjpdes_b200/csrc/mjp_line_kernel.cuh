@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       // the warp have something to generate (or every active lane has), not whenever one lane does.
       const MaskT need_l = live ? need : (MaskT)0;           // (a lane that has just parked or ended touches nothing)
       const unsigned needm = __ballot_sync(am, need_l != 0);
-      if (__popc(needm) >= 8 || needm == am) {
+      if (__popc(needm) >= p.refill_lanes || needm == am) {
         for (MaskT q = need_l; __any_sync(am, q != 0);) if (q) {
           const int i = MO::ffs(q); q &= q - 1;
           const bool pending_is_up = !((up ^ dup) & MJP_BIT(i));

@@ -80,6 +80,7 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   }
   kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
   kp.stage_cap = L->log ? 3 * M + 8 : 0;
+  kp.refill_lanes = 8;
   pl.per_thread_bytes = plan_layout(kp, false, true, L->log != 0);   // the largest variant
   return pl;
 }
