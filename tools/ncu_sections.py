@@ -36,7 +36,7 @@ def main():
                ("byte get/set, params", find("auto getb"), find("double r_end[")),
                ("get_end/set_end", find("double r_end["), find("auto px =")),
                ("next_event_time", find("auto next_event_time"), find("// ---- preprocess-model")),
-               ("rescan_fut", find("auto rescan_fut"), find("if (active) rescan_fut();")),
+               ("rescan_fut", find("auto rescan_fut"), find("if (fresh_start) rescan_fut();")),
                ("mark_seen/toggle/type_from", find("auto mark_seen"), find("// ---- SCADA capture")),
                ("out-of-line generators", find("sojourn_counter(uint32_t idx"), find("#define MJP_BIT"))]
     agg = {}
