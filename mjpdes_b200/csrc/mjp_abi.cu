@@ -49,9 +49,8 @@ struct mjp_handle {
   // uploaded line
   bool uploaded = false, launched = false, sweep = false;
   mjp::KParams kp{};
-  std::vector<int32_t> Ncap;
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_stage, d_cold, d_park, d_tapes;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -218,7 +217,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_stage, &h->d_cold, &h->d_park, &h->d_tapes})
+                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -239,7 +238,6 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   mjp::KParams &kp = h->kp;
   kp = pl.kp;
   const int R = kp.R, levels = kp.L;
-  h->Ncap.assign(L->N, L->N + (M - 1));
 
   // ---- constants: lam mu W w dur thr | N lvl ----
   const size_t dbytes = pl.cd.size() * sizeof(double), ibytes = pl.ci.size() * sizeof(int32_t);

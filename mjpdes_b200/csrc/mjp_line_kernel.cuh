@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     return c_dur[k * M + i];
   };
 
-  double r_end[MT > 0 ? MT : 1];
+  double r_end[MT > 0 ? MT : 1] = {};
   auto get_end = [&](int i) -> double {
     if (MT > 0) {
       double v = r_end[0];

@@ -9,7 +9,6 @@ struct KParams {
   uint64_t n_inst;        // instances in this launch
   uint64_t first_id;      // RNG instance id of instance 0
   uint64_t seed;
-  uint64_t max_iter;      // watchdog on loop iterations per instance
   // line (flat form of the preprocessed Model, core.clj:578-615)
   int32_t M, K;
   int32_t R;              // job ring size: power of two >= M + sum N (jobs in the line)

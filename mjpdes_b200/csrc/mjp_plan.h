@@ -59,14 +59,6 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   int R = 4;
   while (R < M + sumN) R <<= 1;        // jobs in the line <= M + sum N
   kp.R = R;
-  {
-    // watchdog: the loop makes ~1.3 iterations per machine per time unit; allow far more
-    double rate = 0.0;
-    for (int i = 0; i < M; ++i) rate += 4.0 + L->lambda[i] + L->mu[i];
-    double it = 512.0 * (L->run_to + 1.0) * rate + 1e6;
-    if (L->run_to_job >= 0) it += 64.0 * (double)L->run_to_job * M;
-    kp.max_iter = it > 4.29e9 ? 0xFFFFFFFFull : (uint64_t)it;      // the kernel counts iterations in 32 bits
-  }
   pl.cd.insert(pl.cd.end(), L->lambda, L->lambda + M);
   pl.cd.insert(pl.cd.end(), L->mu, L->mu + M);
   pl.cd.insert(pl.cd.end(), L->W, L->W + M);
