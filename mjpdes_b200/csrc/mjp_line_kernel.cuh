@@ -188,12 +188,17 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     uint32_t wd = base[(idx >> 2) * stride];
     base[(idx >> 2) * stride] = (wd & ~(0xFFu << sh)) | (v << sh);
   };
+  // tick / loop flags share one register: F_EJ this tick has an :ej, F_TICK TICKCLK == clock,
+  // F_OVF a per-tick structure overflowed
+  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8, F_TAPE = 16, F_DURPL = 32, F_CAPPL = 64 };   // F_PAUSE: stopped at a slice boundary; F_TAPE: a draw tape ran out
+  // F_DURPL / F_CAPPL: per-instance W or w planes / capacity planes are present (run-time override planes)
+  uint32_t flags = ((p.W_i || p.w_i) ? F_DURPL : 0u) | (p.N_i ? F_CAPPL : 0u);
   // line parameters, with the optional per-instance planes
   auto lam_of = [&](int i) -> double { return (p.lam_i != nullptr) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
   auto mu_of = [&](int i) -> double { return (p.mu_i != nullptr) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
-  auto cap_of = [&](int b) -> int { return (p.N_i != nullptr) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
+  auto cap_of = [&](int b) -> int { return (flags & F_CAPPL) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
   auto dur_of = [&](int k, int i) -> double {
-    if (p.W_i || p.w_i) {
+    if (flags & F_DURPL) {
       const double wv = p.w_i ? p.w_i[(size_t)(k * M + i) * n_inst + g] : p.w[k * M + i];
       const double Wv = p.W_i ? p.W_i[(size_t)i * n_inst + g] : p.W[i];
       return __ddiv_rn(wv, Wv);
@@ -310,11 +315,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // started in the same tick); a third toggle is reported as MJP_INST_TICK_OVERFLOW.
   MaskT pB = 0, twoB = 0, pS = 0, twoS = 0;
   // steady accumulators kept in registers
-  // tick / loop flags share one register: F_EJ this tick has an :ej, F_TICK TICKCLK == clock,
-  // F_OVF a per-tick structure overflowed
-  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8, F_TAPE = 16 };   // F_PAUSE: stopped at a slice boundary; F_TAPE: a draw tape ran out
-  uint32_t flags = 0;
-  auto finish = [&](int code) { p.status[g] = (uint8_t)code; };     // the instance ends with this :status
+  // The instance ends with this :status.  Kept in bits 8.. of `flags` and stored once after the loop: the
+  // rare paths that end an instance are if-converted, and a predicated global store at each of them was
+  // ~30 issued instructions per micro-step.
+  auto finish = [&](int code) { flags = (flags & 0xFFu) | ((uint32_t)(code + 1) << 8); };
   if (REPLAY && fresh_start)
     for (int i = 0; i < M; ++i) if (!(FUT_T(i) == FUT_T(i))) flags |= F_TAPE;   // a tape too short for the first event
 
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   D(clock)                                                                                                  \
   MK(up) MK(occ) MK(B) MK(S) MK(full) MK(empty) MK(pend) MK(dup) MK(fired) MK(need)                         \
   MK(seen) MK(lead) MK(has_bj) MK(has_sm) MK(rtbj) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc)                \
-  U(curjob) U(n_ev) U(flags) U(type_cache)
+  U(curjob) U(n_ev) U(flags) U(type_cache)   /* (flags is parked before the :status code is put into it) */
   // state that exists only in some variants (parking it unconditionally would keep it alive everywhere)
 #define MJP_PARK_LOG(D, U) D(aj_ends) U(line_cnt) U(n_staged)
   auto park_save = [&]() {
@@ -820,6 +824,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     park_save();
     finish(MJP_INST_PAUSED);
   }
+  if (flags >> 8) p.status[g] = (uint8_t)((flags >> 8) - 1);
 
   // the reference never flushes the last tick: whatever is still in :log-buf is lost
   if (p.final_clock) p.final_clock[g] = clock;
