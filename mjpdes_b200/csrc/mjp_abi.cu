@@ -296,18 +296,7 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   CK(h->d_scratch.reserve(n * (size_t)R * 8));
   kp.enters = h->d_scratch.as<double>();
 
-  // ---- launch shape ----
-  const size_t per_thread = pl.per_thread_bytes;
-  int threads = 0;
-  // 64-thread CTAs: a batch is one wave of equally long instances, so the step time is set by the
-  // fullest SM; small CTAs spread 100 000 instances over 148 SMs within 4 % of the mean.
-  for (int t : {64, 32}) {
-    if ((size_t)kp.const_bytes + per_thread * t <= h->smem_optin) { threads = t; break; }
-  }
-  if (!threads) return fail(h, MJP_ERR_UNSUPPORTED, "line state does not fit in shared memory (M, sum N too large)");
-  h->block_threads = threads;
-  h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
-
+  // the launch shape (layout, CTA size) depends on the kernel variant and is chosen in mjp_launch_slice
   // aggregate scratch
   h->agg_blocks = h->sm_count > 0 ? h->sm_count : 148;
   const int len = mjp_aggregate_len(M);
@@ -382,21 +371,35 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
   const bool replay = rng->mode != MJP_RNG_COUNTER, hash = (h->flags & MJP_CFG_EVENT_HASH) != 0;
   if (h->want_log && !kp.log_records) return fail(h, MJP_ERR_INVALID, "SCADA capture wanted: call mjp_reserve_log first");
   {
-    int threads = h->block_threads;
-    const bool mt = use_register_ends(kp, h->want_log, threads);
-    size_t per_thread = mjp::plan_layout(kp, mt, replay, h->want_log, false);
-    // Wide lines: when shared memory would hold fewer than 6 CTAs of 64 threads per SM, keep only the
-    // per-micro-step state on chip and the rest in an L2-resident scratch (COLD variants).
+    // Launch shape.  64-thread CTAs spread a batch of equally long instances evenly over the SMs (the step
+    // time is set by the fullest SM).  Wide lines: when shared memory would hold fewer than 6 such CTAs per SM
+    // AND the batch needs more than one wave, only the per-micro-step state stays on chip and the rest goes
+    // to an L2-resident scratch (COLD variants); otherwise the extra latency is not worth it.  If nothing
+    // else fits, COLD and/or 32-thread CTAs are the fallback.
     static const char *cold_env = std::getenv("MJP_COLD");            // A/B measurements: 0 = never, 1 = always
-    // ... but only when the batch is large enough to need the extra residency (otherwise it only adds latency)
-    const size_t cta_bytes = (size_t)kp.const_bytes + per_thread * threads + 1024;
-    const size_t resident = (size_t)(h->sm_count > 0 ? h->sm_count : 148) * (h->smem_optin / cta_bytes);
-    bool cold = !mt && (size_t)kp.const_bytes + per_thread * 64 + 1024 > h->smem_optin / 6 &&
-                (kp.n_inst + threads - 1) / threads > resident;
-    if (cold_env) cold = !mt && cold_env[0] == '1';
-    if (cold) {
+    const size_t sms = (size_t)(h->sm_count > 0 ? h->sm_count : 148);
+    auto cta_bytes = [&](bool c, int t) {
+      mjp::KParams tmp = kp;
+      const bool mt_ = !c && use_register_ends(kp, h->want_log, t);
+      return (size_t)kp.const_bytes + mjp::plan_layout(tmp, mt_, replay, h->want_log, c) * t;
+    };
+    auto fits = [&](bool c, int t) { return cta_bytes(c, t) <= h->smem_optin; };
+    int threads = 0;
+    bool cold = false;
+    if (fits(false, 64)) {
       threads = 64;
-      per_thread = mjp::plan_layout(kp, false, replay, h->want_log, true);
+      const size_t per_sm = h->smem_optin / (cta_bytes(false, 64) + 1024);
+      const bool register_ends = use_register_ends(kp, h->want_log, 64);
+      cold = !register_ends && per_sm < 6 && (kp.n_inst + 63) / 64 > sms * per_sm && fits(true, 64);
+      if (cold_env) cold = !register_ends && cold_env[0] == '1' && fits(true, 64);
+    } else if (fits(true, 64)) { threads = 64; cold = true; }
+    else if (fits(false, 32)) { threads = 32; }
+    else if (fits(true, 32)) { threads = 32; cold = true; }
+    else return fail(h, MJP_ERR_UNSUPPORTED, "line state does not fit in shared memory (M, sum N too large)");
+    h->block_threads = threads;
+    const bool mt = !cold && use_register_ends(kp, h->want_log, threads);
+    const size_t per_thread = mjp::plan_layout(kp, mt, replay, h->want_log, cold);
+    if (cold) {
       const size_t fb = mjp::plan_align_up((size_t)mjp::cold_f64_slots(kp) * kp.n_inst * 8, 256);
       CK(h->d_cold.reserve(fb + (size_t)mjp::cold_u32_slots(kp, replay) * kp.n_inst * 4));
       kp.cold_f = h->d_cold.as<double>();

@@ -71,7 +71,11 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
     for (int k = 0; k < K; ++k) { pl.cd.push_back(accum); accum = accum + L->portion[k]; }
   }
   kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
-  kp.stage_cap = L->log ? 3 * M + 8 : 0;
+  // SCADA capture stages one tick of messages per instance.  A machine logs at most nine messages in a tick
+  // (complete, start, :bl, :ub, :st, :us, :up, :down and a re-fired :up/:down); the cleaned-order list holds
+  // one byte per message, hence the cap of 255 (beyond it: MJP_INST_TICK_OVERFLOW, lines of >= 28 machines
+  // on which nearly every machine acts at the same instant).
+  kp.stage_cap = L->log ? (9 * M + 4 < 255 ? 9 * M + 4 : 255) : 0;
   kp.refill_lanes = 8;
   pl.per_thread_bytes = plan_layout(kp, false, true, L->log != 0);   // the largest variant
   return pl;
