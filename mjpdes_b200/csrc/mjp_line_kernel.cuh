@@ -352,6 +352,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   uint32_t line_cnt = 0;                                   // [:report :line-cnt]
   double aj_ends = 0.0;
   auto stage_msg = [&](int act, int m, int n, uint32_t job) {      // log/log util/log.clj:30-36
+    // print-now? (util/log.clj:220-226) is constant within a tick: a tick before the warm-up or after
+    // :max-lines has been reached is never printed, so there is nothing to stage for it
+    if (clock < p.warm_up || (uint64_t)line_cnt >= p.max_lines) return;
     if (n_staged < stage_cap)
       s_stage[n_staged * nt] = (unsigned long long)act | ((unsigned long long)m << 8) |
                                ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);

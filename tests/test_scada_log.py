@@ -126,3 +126,16 @@ def test_gpu_c4_shape_log_volume(engine):
     assert np.all(log["clk"] >= line.warm_up)
     # every action logs one message; cancelled :bl/:ub and :st/:us pairs and the warm-up are the only losses
     assert np.all(per <= got.stats.n_events) and per.sum() > 0.75 * got.stats.n_events.sum() * (1000.0 / 1100.0)
+
+
+def test_lattice_line_fills_a_tick_with_messages(oracle):
+    """Identical machines on a w/W lattice: nearly every machine acts at the same instants, ~5 messages per
+    machine per tick (found by differential fuzzing: the staging area must hold 9 per machine)."""
+    from hostsim import binding as H
+    line = abi.HostLine(lam=[.1] * 16, mu=[.9] * 16, W=[1.] * 16, discipline=[0] * 16, N=[2] * 15, portion=[1.],
+                        w=np.ones((1, 16)), warm_up=0, run_to=150, log=True, max_lines=abi.UINT64_MAX)
+    want = oracle.run(line, 2, seed=957, log_capacity=300_000)
+    assert want.extra["max_tick_msgs"].max() > 3 * 16 + 8
+    got = H.run(line, 2, seed=957, log_capacity=300_000)
+    assert set(got.status.tolist()) == {abi.INST_NORMAL_END}
+    assert_same_log(got.log, want.log)
