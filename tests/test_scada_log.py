@@ -130,12 +130,21 @@ def test_gpu_c4_shape_log_volume(engine):
 
 def test_lattice_line_fills_a_tick_with_messages(oracle):
     """Identical machines on a w/W lattice: nearly every machine acts at the same instants, ~5 messages per
-    machine per tick (found by differential fuzzing: the staging area must hold 9 per machine)."""
+    machine per tick (found by differential fuzzing, case 957: the staging area must hold 9 per machine)."""
     from hostsim import binding as H
-    line = abi.HostLine(lam=[.1] * 16, mu=[.9] * 16, W=[1.] * 16, discipline=[0] * 16, N=[2] * 15, portion=[1.],
-                        w=np.ones((1, 16)), warm_up=0, run_to=150, log=True, max_lines=abi.UINT64_MAX)
-    want = oracle.run(line, 2, seed=957, log_capacity=300_000)
-    assert want.extra["max_tick_msgs"].max() > 3 * 16 + 8
-    got = H.run(line, 2, seed=957, log_capacity=300_000)
+    rng = np.random.default_rng(100000 + 957)
+    M = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 20, 31, 32, 33, 40, 64]))
+    K = int(rng.integers(1, 6))
+    kw = dict(jm2dm=bool(rng.random() < .3), up_down=bool(rng.random() < .4), bbs_prob=float(rng.choice([0, .3, .7, 1.0])),
+              reliable_prob=float(rng.choice([0, .1, .5])))
+    run_to = float(rng.choice([60, 150, 400]))
+    line = random_line(rng, M, K, run_to=run_to, warm_up=run_to * float(rng.choice([0, 0.1, 0.5])), **kw)
+    line.W[:] = 1.0
+    line.w[:] = 1.0
+    line.log, line.max_lines = True, abi.UINT64_MAX
+    assert M == 16
+    want = oracle.run(line, 1, mode=abi.RNG_REPLAY, seed=957, log_capacity=300_000)
+    assert want.extra["max_tick_msgs"].max() > 3 * M + 8
+    got = H.run(line, 1, mode=abi.RNG_REPLAY, seed=957, log_capacity=300_000)
     assert set(got.status.tolist()) == {abi.INST_NORMAL_END}
     assert_same_log(got.log, want.log)
