@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
 #define CNT(b)     su[(hu + (b)) * nt]          /* (count :holding) of buffer b       */
   uint32_t *s_jt = cup + (size_t)(COLD ? 2 * M : 3 * M - 1) * cs;  /* job type ring, 4 per word    */
-  uint32_t *s_eidx = s_jt + (size_t)(p.R >> 2) * cs;              /* REPLAY only: exponential cursor */
+  const int jtw = K > 1 ? (p.R >> 2) : 0;                         /* a single job type needs no ring */
+  uint32_t *s_eidx = s_jt + (size_t)jtw * cs;                     /* REPLAY only: exponential cursor */
   const uint32_t Rm = (uint32_t)p.R - 1;
 
   auto getb = [&](uint32_t *base, size_t stride, int idx) -> uint32_t {
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   unsigned long long *s_stage =
       reinterpret_cast<unsigned long long *>(sf + (size_t)(hb + 3 + (MT > 0 ? 0 : M)) * nt);
   // cleaned order, 4 indices per word: after the hot u32 slots (and the cold ones when they share the array)
-  uint32_t *s_ord = su + (size_t)(COLD ? M - 1 : 3 * M - 1 + (p.R >> 2) + (REPLAY ? M : 0)) * nt;
+  uint32_t *s_ord = su + (size_t)(COLD ? M - 1 : 3 * M - 1 + jtw + (REPLAY ? M : 0)) * nt;
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
   uint32_t line_cnt = 0;                                   // [:report :line-cnt]
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
             }
           }
           curjob = id; occ |= 1; STARTED(0) = id;
-          setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
+          if (K > 1) setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
           p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
           if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
         }
@@ -782,7 +783,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       const int b = i - 1;
       const int n = (int)CNT(b);
       const uint32_t id = STARTED(i) + 1;
-      const int type = (int)getb(s_jt, cs, (int)(id & Rm));
+      const int type = K > 1 ? (int)getb(s_jt, cs, (int)(id & Rm)) : 0;
       start_job(i, type);
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);

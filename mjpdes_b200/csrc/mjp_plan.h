@@ -34,7 +34,9 @@ inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX ORD);
 // with it they live in a global scratch of cold_f64_slots / cold_u32_slots rows per instance.
 inline int cold_f64_slots(const KParams &kp) { return 5 * kp.M - 1; }
-inline int cold_u32_slots(const KParams &kp, bool replay) { return 2 * kp.M + (kp.R >> 2) + (replay ? kp.M : 0); }
+inline int cold_u32_slots(const KParams &kp, bool replay) {
+  return 2 * kp.M + (kp.K > 1 ? (kp.R >> 2) : 0) + (replay ? kp.M : 0);      // no job-type ring for a single type
+}
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
   kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
