@@ -21,13 +21,26 @@
 //    resolved when the machine's next :up event fires -- the same f64 operations in
 //    the same order as core.clj:145-151, so :ends is bit-identical, and every
 //    up/down event is generated exactly once;
+//  * the NEXT up/down event of a machine is pre-generated lazily, out of line, when at
+//    least 8 lanes of the warp have one to generate (Philox + ln is ~200 instructions
+//    that only ~5 % of the events need);
 //  * a clock tick's messages are not stored: what clean-log-buf + add-compute-log!
-//    would do with them is a function of (machines seen, in which order; toggle
-//    counts of :bl/:ub and :st/:us per machine; which buffers got a :bj / :sm),
-//    all kept as bitmasks and applied when the next tick's first message arrives;
+//    would do with them is a function of (machines seen, in which order; parity of
+//    :bl/:ub and :st/:us per machine -- a pair cancels; which buffers got a :bj / :sm),
+//    all kept as bitmasks and applied when the next tick's first message arrives
+//    (with LOG the messages ARE staged, in shared memory, and written as records);
 //  * accumulators are added straight into the caller-visible output planes with
 //    fire-and-forget RED.ADD.F64 (one writer per address: order and rounding are
 //    those of the sequential sum).
+//
+// Execution model: one micro-step (one trip of the reference's loop/recur) per trip of the
+// kernel loop, the warp in lock-step; every batch section is a loop voted with __any_sync
+// over the lanes that are active in this trip, and no lane leaves the body early -- without
+// this the lanes of a warp drift apart for good (ncu: 3.9 of 32 lanes per instruction).
+// All instances of a batch take the same time, so the batch must be ONE wave: <= 80
+// registers and <= ~19 KB of shared memory per 64-thread CTA (11-12 CTAs per SM) are hard
+// constraints, which is why the generators are out of line, the shared layout is sized per
+// variant, and slicing / tapes / SCADA capture / wide-line (COLD) layouts are variants.
 #pragma once
 #include "mjp_device.cuh"
 #include "mjp_params.h"
@@ -189,10 +202,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     uint32_t wd = base[(idx >> 2) * stride];
     base[(idx >> 2) * stride] = (wd & ~(0xFFu << sh)) | (v << sh);
   };
-  // tick / loop flags share one register: F_EJ this tick has an :ej, F_TICK TICKCLK == clock,
-  // F_OVF a per-tick structure overflowed
-  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8, F_TAPE = 16, F_DURPL = 32, F_CAPPL = 64 };   // F_PAUSE: stopped at a slice boundary; F_TAPE: a draw tape ran out
-  // F_DURPL / F_CAPPL: per-instance W or w planes / capacity planes are present (run-time override planes)
+  // Tick / loop flags share one register (bits 0-7; bits 8.. hold the end status, see finish()):
+  //   F_EJ     this tick has an :ej                    F_TICK   TICKCLK == clock
+  //   F_OVF    a per-tick structure overflowed         F_PAUSE  stopped at a slice boundary
+  //   F_TAPE   a draw tape ran out                     F_DURPL / F_CAPPL  per-instance W|w / N planes are present
+  enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8, F_TAPE = 16, F_DURPL = 32, F_CAPPL = 64 };
   uint32_t flags = ((p.W_i || p.w_i) ? F_DURPL : 0u) | (p.N_i ? F_CAPPL : 0u);
   // line parameters, with the optional per-instance planes
   auto lam_of = [&](int i) -> double { return (p.lam_i != nullptr) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
@@ -315,7 +329,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // toggle three times in one tick while processing times are positive (it would have to finish a job it
   // started in the same tick); a third toggle is reported as MJP_INST_TICK_OVERFLOW.
   MaskT pB = 0, twoB = 0, pS = 0, twoS = 0;
-  // steady accumulators kept in registers
   // The instance ends with this :status.  Kept in bits 8.. of `flags` and stored once after the loop: the
   // rare paths that end an instance are if-converted, and a predicated global store at each of them was
   // ~30 issued instructions per micro-step.
@@ -579,7 +592,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const MaskT c_blb = bbs & ~B & ~occ & nonempty & full;     // BBS, time = clock          core.clj:387-394,406-411
     const MaskT c_bla = ~bbs & ~B & full & occ & ~pend & ALL;  // BAS, time = :ends          core.clj:376-383,401-405
     const MaskT c_tb = occ & ~B & notfull & ~pend & ALL;       // time = max(clock, :ends)   core.clj:472-483
-    const MaskT st_chk = ~S & empty & occ & ~pend;             // finished? needs clock >= :ends, utils.clj:68-74
 
     // Machines whose job is already over (clock >= :ends).  For them max(clock, :ends) = clock, so their
     // advance2buffer candidate is a "now" candidate; a BAS new-blocked candidate that is late has
@@ -590,7 +602,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     for (int i = 0; i < (MT > 0 ? MT : M); ++i)
       if (clock >= (MT > 0 ? r_end[i] : ENDS_S(i))) late |= MJP_BIT(i);
     late &= occ & ~pend;
-    const MaskT c_st = ~S & empty & (~occ | late) & ALL;                                      // core.clj:451-460
+    const MaskT c_st = ~S & empty & (~occ | late) & ALL;       // finished? = no job or clock >= :ends   core.clj:451-460, utils.clj:68-74
     const MaskT tb_now = c_tb & late, bl_now = c_bla & late, fut = (c_tb | c_bla) & ~late;
     const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup | tb_now | bl_now) != 0;
 
