@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define ENDS_S(i)  sf[(hb + 3 + (i)) * nt]      /* :status :ends, or remaining work (MT == 0 only) */
 #define FUT_N(i)   cup[(i) * cs]                 /* :future index                      */
 #define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
-#define CNT(b)     su[(hu + (b)) * nt]          /* (count :holding) of buffer b       */
+#define CNT(b)     su[(hu + (b)) * nt]          /* bits 0-7 (count :holding) of buffer b; bits 8.. this tick's
+                                                   occupancy bookkeeping, see buffer_tick_bits            */
   uint32_t *s_jt = cup + (size_t)(COLD ? 2 * M : 3 * M - 1) * cs;  /* job type ring, 4 per word    */
   const int jtw = K > 1 ? (p.R >> 2) : 0;                         /* a single job type needs no ring */
   uint32_t *s_eidx = s_jt + (size_t)jtw * cs;                     /* REPLAY only: exponential cursor */
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   uint32_t n_ev = 0;                            // run-action calls not yet added to p.n_events
   uint64_t h = 0xcbf29ce484222325ull;
   // tick state (what :log-buf holds, util/log.clj:89-109)
-  MaskT seen = 0, lead = 0, has_bj = 0, has_sm = 0, rtbj = 0;
+  MaskT seen = 0, lead = 0, touched = 0;       // touched: buffers with a :bj / :sm in this tick
   // :bl/:ub (resp. :st/:us) messages of the tick per machine: parity and "two seen".  A machine cannot
   // toggle three times in one tick while processing times are positive (it would have to finish a job it
   // started in the same tick); a third toggle is reported as MJP_INST_TICK_OVERFLOW.
@@ -344,6 +345,22 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const MaskT next_seen = (MaskT)0 - (((seen >> 1) >> i) & 1);   // all-ones iff machine i+1 logged already
     lead = (lead & ~fresh) | (fresh & ~next_seen);
     seen |= bit;
+  };
+  // buf+ / buf- (util/log.clj:159-171): of the messages a tick puts on a buffer, the FIRST IN CLEANED ORDER
+  // gets the elapsed time at its level n, the others add (clk - clk) = 0.  A buffer sees at most one :bj (from
+  // machine b) and one :sm (from machine b+1) per tick; cleaned order is by machine in order of first
+  // appearance (util/log.clj:44), so when both occur the winner is decided by `lead`.  The winning level is
+  // kept in bits 8-15 of the count word; bit 16 = first message was the :bj, bit 17 = one message so far,
+  // bit 18 = two.  Stale bits of an older tick are overwritten by the first message of a new one.
+  auto buffer_tick_bits = [&](uint32_t w, MaskT bbit, int n, bool is_bj, bool precedes) -> uint32_t {
+    if (!(touched & bbit)) {
+      touched |= bbit;
+      return ((uint32_t)n << 8) | (is_bj ? 0x10000u : 0u) | 0x20000u;
+    }
+    uint32_t hi = w & 0xFFFFFF00u;
+    if ((((hi >> 16) & 1u) != 0) == is_bj || (hi & 0x40000u)) flags |= F_OVF;   // same kind twice, or a third message
+    if (precedes) hi = (hi & 0xFFFF00FFu) | ((uint32_t)n << 8);
+    return hi | 0x40000u;
   };
   auto toggle = [&](MaskT &par, MaskT &two, MaskT bit) {
     if (two & bit) flags |= F_OVF;
@@ -471,17 +488,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       for (MaskT q = warm ? pB : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, false); }
       for (MaskT q = warm ? pS : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, true); }
     }
-    // buf+ / buf- (util/log.clj:159-171): the first message on a buffer in cleaned order gets the
-    // elapsed time, the others add (clk - clk) = 0.
-    for (MaskT q = warm ? (has_bj | has_sm) : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
+    // buf+ / buf-: one RED per touched buffer, at the level recorded by buffer_tick_bits
+    for (MaskT q = warm ? touched : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
       const int b = MO::ffs(q); q &= q - 1;
-      const int cf = (int)CNT(b);
-      const bool bj = (has_bj >> b) & 1, sm = (has_sm >> b) & 1, bj_first_rt = (rtbj >> b) & 1;
-      // levels seen by the :bj and the :sm of this tick, from the final count cf
-      const int n_bj = sm ? (bj_first_rt ? cf : cf - 1) : cf - 1;
-      const int n_sm = bj ? (bj_first_rt ? cf + 1 : cf) : cf + 1;
-      const bool take_bj = bj && (!sm || ((lead >> b) & 1));   // machine b logged before machine b+1?
-      const int n = take_bj ? n_bj : n_sm;
+      const int n = (int)((CNT(b) >> 8) & 0xFFu);
       const double lc = LASTCLK(b);
       red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
       LASTCLK(b) = tick_clk;
@@ -498,7 +508,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       }
     }
     if (LOG) emit_tick(fm, tick_clk);
-    seen = lead = has_bj = has_sm = rtbj = 0;
+    seen = lead = touched = 0;
     pB = twoB = pS = twoS = 0;
     flags &= ~(uint32_t)F_EJ;
   };
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define MJP_PARK_LIST(D, MK, U, Q)                                                                          \
   D(clock)                                                                                                  \
   MK(up) MK(occ) MK(B) MK(S) MK(full) MK(empty) MK(pend) MK(dup) MK(fired) MK(need)                         \
-  MK(seen) MK(lead) MK(has_bj) MK(has_sm) MK(rtbj) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc)                \
+  MK(seen) MK(lead) MK(touched) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc)                \
   U(curjob) U(n_ev) U(flags) U(type_cache)   /* (flags is parked before the :status code is put into it) */
   // state that exists only in some variants (parking it unconditionally would keep it alive everywhere)
 #define MJP_PARK_LOG(D, U) D(aj_ends) U(line_cnt) U(n_staged)
@@ -769,14 +779,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       const MaskT bit = MJP_BIT(i);
       const uint32_t id = STARTED(i);
       if (i < M - 1) {
-        const int n = (int)CNT(i);
+        const uint32_t cw = CNT(i);
+        const int n = (int)(cw & 0xFFu);
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
-        if (has_bj & bit) flags |= F_OVF;
-        has_bj |= bit;
-        rtbj |= bit & ~has_sm;
-        CNT(i) = (uint32_t)(n + 1);
+        CNT(i) = (uint32_t)(n + 1) | buffer_tick_bits(cw, bit, n, true, ((lead >> i) & 1) != 0);
         if (n + 1 == cap_of(i)) full |= bit;
         empty &= ~(bit << 1);
       } else {
@@ -793,16 +801,15 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       const int i = MO::ffs(q); q &= q - 1;
       const MaskT bit = MJP_BIT(i), bbit = bit >> 1;
       const int b = i - 1;
-      const int n = (int)CNT(b);
+      const uint32_t cw = CNT(b);
+      const int n = (int)(cw & 0xFFu);
       const uint32_t id = STARTED(i) + 1;
       const int type = K > 1 ? (int)getb(s_jt, cs, (int)(id & Rm)) : 0;
       start_job(i, type);
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);
       if (LOG) stage_msg(MJP_ACT_SM, i, n, id);
-      if (has_sm & bbit) flags |= F_OVF;
-      has_sm |= bbit;
-      CNT(b) = (uint32_t)(n - 1);
+      CNT(b) = (uint32_t)(n - 1) | buffer_tick_bits(cw, bbit, n, false, ((lead >> b) & 1) == 0);
       if (n - 1 == 0) empty |= bit;
       full &= ~bbit;
       occ |= bit; STARTED(i) = id;
