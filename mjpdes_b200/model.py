@@ -318,14 +318,42 @@ def calc_bneck(res: dict, machines: list) -> dict:
     return {**res, ":bottleneck-machine": machines[sev.index(max(sev))]}
 
 
+def calc_residence_time(res: dict, cl: CompiledLine, inst: int = 0) -> dict:
+    """core.clj:663-700 (dormant in the reference: ``#_`` in analyze-results, core.clj:706).  Adds
+    ``:computed-residence-time`` per job type from machine efficiencies mu/(lambda+mu), w/W (job-requires,
+    utils.clj:95-101), the measured blocked fractions and the occupancy of each machine's feed buffer."""
+    host, M = cl.host, cl.host.M
+    lam = host.lam_inst[:, inst] if host.lam_inst is not None else host.lam
+    mu = host.mu_inst[:, inst] if host.mu_inst is not None else host.mu
+    W = host.W_inst[:, inst] if host.W_inst is not None else host.W
+    w = host.w_inst[:, inst].reshape(host.K, M) if host.w_inst is not None else host.w
+    eff = [float(mu[i]) / (float(lam[i]) + float(mu[i])) for i in range(M)]
+    requires = [[float(w[k, i]) / float(W[i]) for i in range(M)] for k in range(host.K)]
+    virt = [sum(float(host.portion[k]) * (1.0 / eff[i]) * requires[k][i] for k in range(host.K)) for i in range(M)]
+    bl = [res[":blocked"][m] for m in cl.machines]
+    computed = {}
+    for k, jt in enumerate(cl.jobtypes):
+        processing = sum((1.0 / eff[i]) * (1.0 + bl[i]) * requires[k][i] for i in range(M))
+        waiting = sum((0.5 + res[":avg-buffer-occupancy"][cl.buffers[i - 1]]) * virt[i] * (1.0 + bl[i])
+                      for i in range(1, M))                        # 0 for the entry machine, core.clj:693-694
+        computed[jt] = processing + waiting
+    return {**res, ":computed-residence-time": computed}
+
+
 def analyze_results(cl: CompiledLine, stats: abi.HostStats, inst: int) -> dict:
     return calc_bneck(calc_basics(cl, stats, inst), cl.machines)          # core.clj:702-706
 
 
-def postprocess_model(cl: CompiledLine, stats: abi.HostStats, inst: int, process_id: int, wall_seconds: float) -> dict:
-    """core.clj:708-718, plus the README's key aliases."""
+def postprocess_model(cl: CompiledLine, stats: abi.HostStats, inst: int, process_id: int, wall_seconds: float,
+                      log: np.ndarray | None = None) -> dict:
+    """core.clj:708-718, plus the README's key aliases.  With ``:report {:diag-log-buf? true}`` the
+    result carries ``:diag-log-buf``: every message print-lines saw, without ``:line`` (util/log.clj:134-135)."""
     r = analyze_results(cl, stats, inst)
     r[":process-id"] = process_id
+    if (cl.model.get(":report") or {}).get(":diag-log-buf?"):
+        from . import scada
+        msgs = scada.pull_data(cl, log, None, instance=inst) if log is not None else []
+        r[":diag-log-buf"] = [{k: v for k, v in m.items() if k != ":line"} for m in msgs]
     r[":jobmix"] = {jt: dict(cl.model[":jobmix"][jt]) for jt in cl.jobtypes}
     r[":status"] = abi.INST_STATUS_KEYWORD.get(int(stats.status[inst]), ":unknown")
     r[":runtime"] = wall_seconds
@@ -361,7 +389,7 @@ def main_loop(model: dict, handle=None, out_stream=None, seed: int = DEFAULT_SEE
         if own:
             h.close()
     wall = time.time() - start
-    results = [postprocess_model(cl, res.stats, g, g if n > 1 else 1, wall) for g in range(n)]
+    results = [postprocess_model(cl, res.stats, g, g if n > 1 else 1, wall, log=res.log) for g in range(n)]
     if out_stream is not None:
         out_stream.write("#_" + scada.pprint_edn(scada.pretty_model(model)) + "\n")      # core.clj:751-752,774-775
         if res.log is not None:

@@ -101,8 +101,8 @@ def render_lines(cl, records: np.ndarray, instance: int | None = None):
     return [format_line(message_map(cl, r)) for r in recs]
 
 
-def pull_data(cl, records: np.ndarray, n: int, instance: int = 0):
-    """core/pull-data! (core.clj:845-849) over a captured stream: the first n message maps."""
+def pull_data(cl, records: np.ndarray, n: int | None, instance: int = 0):
+    """core/pull-data! (core.clj:845-849) over a captured stream: the first n message maps (all if n is None)."""
     recs = np.sort(records[records["instance"] == instance], order="line")[:n]
     return [message_map(cl, r) for r in recs]
 

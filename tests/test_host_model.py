@@ -141,6 +141,30 @@ def test_calc_basics_matches_oracle_restatement(oracle):
         assert res[":status"] == ":normal-end" and res[":bneck"] == res[":bottleneck-machine"] in cl.machines
 
 
+def test_calc_residence_time_and_diag_log_buf(oracle):
+    """core.clj:663-700 (dormant in the reference) and :diag-log-buf? (core.clj:585,713-714; util/log.clj:134-135)."""
+    d = dict(GOLDENS["models"]["data/quick.clj"])
+    d[":report"] = {":log?": True, ":max-lines": 50, ":diag-log-buf?": True}
+    cl = model.preprocess_model(as_model(d))
+    r = oracle.run(cl.host, 2, seed=SEED, log_capacity=400)
+    res = model.postprocess_model(cl, r.stats, 1, 1, 0.1, log=r.log)
+    buf = res[":diag-log-buf"]
+    want = scada.pull_data(cl, r.log, None, instance=1)
+    assert len(buf) >= 50 and all(":line" not in m for m in buf)
+    assert [dict(m, **{":line": w[":line"]}) for m, w in zip(buf, want)] == want
+    # hand evaluation for a 2-machine, 1-type line: eff = mu/(lam+mu); w/W; wait = (0.5 + occ b1) * virt m2 * (1+bl m2)
+    d2 = dict(GOLDENS["models"]["data/submodel-1.clj"])
+    cl2 = model.preprocess_model(as_model(d2), n_inst=1)
+    h = cl2.host
+    fake = {":blocked": {cl2.machines[0]: 0.25, cl2.machines[1]: 0.0}, ":avg-buffer-occupancy": {cl2.buffers[0]: 1.5}}
+    got = model.calc_residence_time(fake, cl2)[":computed-residence-time"]
+    eff = [h.mu[i] / (h.lam[i] + h.mu[i]) for i in range(2)]
+    req = [h.w[0, i] / h.W[i] for i in range(2)]
+    virt2 = h.portion[0] * req[1] / eff[1]
+    expect = req[0] / eff[0] * 1.25 + req[1] / eff[1] * 1.0 + (0.5 + 1.5) * virt2 * 1.0
+    assert list(got) == cl2.jobtypes and got[cl2.jobtypes[0]] == pytest.approx(expect, rel=1e-14)
+
+
 # ---- SCADA text ------------------------------------------------------------------------------------------
 
 def _render(oracle, gid, warm_up=0):
