@@ -50,7 +50,7 @@ struct mjp_handle {
   bool uploaded = false, launched = false, sweep = false;
   mjp::KParams kp{};
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -128,19 +128,16 @@ static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int thread
   return cudaGetLastError();
 }
 
-// MT > 0 (register-resident :ends, exactly MT machines) exists without SCADA capture only.
 template <typename MaskT, int MT, bool COLD = false>
 static cudaError_t launch_flags(bool replay, bool hash, bool slice, bool log, const mjp::KParams &kp, int blocks,
                                 int threads, size_t smem, cudaStream_t st) {
   const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (slice ? 1 : 0);
 #define MJP_CASE(n, LG) \
   case n: return launch_variant<MaskT, MT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, LG, COLD>(kp, blocks, threads, smem, st);
-  if constexpr (MT == 0) {
-    if (log) {
-      switch (v) {
-        MJP_CASE(0, true) MJP_CASE(1, true) MJP_CASE(2, true) MJP_CASE(3, true)
-        MJP_CASE(4, true) MJP_CASE(5, true) MJP_CASE(6, true) default: MJP_CASE(7, true)
-      }
+  if (log) {
+    switch (v) {
+      MJP_CASE(0, true) MJP_CASE(1, true) MJP_CASE(2, true) MJP_CASE(3, true)
+      MJP_CASE(4, true) MJP_CASE(5, true) MJP_CASE(6, true) default: MJP_CASE(7, true)
     }
   }
   switch (v) {
@@ -152,7 +149,8 @@ static cudaError_t launch_flags(bool replay, bool hash, bool slice, bool log, co
 
 static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
   static const bool force_generic = std::getenv("MJP_FORCE_GENERIC") != nullptr;   // A/B measurements only
-  return !log && !force_generic && threads == MJP_FIXED_NT && kp.M >= 2 && kp.M <= 8;
+  (void)log;
+  return !force_generic && threads == MJP_FIXED_NT && kp.M >= 2 && kp.M <= 8;
 }
 
 static cudaError_t launch_line_kernel(bool replay, bool hash, bool slice, bool log, bool cold, const mjp::KParams &kp,
@@ -217,7 +215,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes})
+                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -404,6 +402,10 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
       CK(h->d_cold.reserve(fb + (size_t)mjp::cold_u32_slots(kp, replay) * kp.n_inst * 4));
       kp.cold_f = h->d_cold.as<double>();
       kp.cold_u = reinterpret_cast<uint32_t *>((char *)h->d_cold.ptr + fb);
+    }
+    if (h->want_log) {                              // one tick of staged messages per instance; persists across slices
+      CK(h->d_stage.reserve((size_t)kp.stage_cap * kp.n_inst * sizeof(unsigned long long)));
+      kp.stage = h->d_stage.as<unsigned long long>();
     }
     h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
     if (resume || until < std::numeric_limits<double>::infinity()) {   // == slice

@@ -28,7 +28,7 @@
 //    would do with them is a function of (machines seen, in which order; parity of
 //    :bl/:ub and :st/:us per machine -- a pair cancels; which buffers got a :bj / :sm),
 //    all kept as bitmasks and applied when the next tick's first message arrives
-//    (with LOG the messages ARE staged, in shared memory, and written as records);
+//    (with LOG the messages ARE staged, in an L2-resident scratch, and written as records);
 //  * accumulators are added straight into the caller-visible output planes with
 //    fire-and-forget RED.ADD.F64 (one writer per address: order and rounding are
 //    those of the sequential sum).
@@ -62,6 +62,73 @@ __device__ __forceinline__ void hmix(uint64_t &h, uint64_t w) { h = (h ^ w) * 0x
 
 // fire-and-forget add into an output plane
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+// ---- SCADA records (LOG) -------------------------------------------------------------------------
+// class of a message for clean-log-buf (util/log.clj:46-56): 0 = :bl/:ub, 1 = :st/:us, 2 = the rest
+__device__ __forceinline__ unsigned log_class(unsigned act) {
+  return (act == MJP_ACT_BL || act == MJP_ACT_UB) ? 0u : ((act == MJP_ACT_ST || act == MJP_ACT_US) ? 1u : 2u);
+}
+struct LogTick {                       // what the records of one tick of one instance have in common
+  mjp_log_record *out;
+  unsigned long long base, capacity;   // first reserved record, size of the record buffer
+  double clk, aj_ends, ej_ent;
+  uint32_t line_cnt, inst;
+  int k;                               // records reserved for this tick
+};
+// record number q of the tick from staged word w (act | m << 8 | n << 16 | job << 32).
+// Returns 0 = written, 1 = buffer full (dropped), 2 = more records than reserved.
+__device__ __forceinline__ int put_record(const LogTick &t, int q, unsigned long long w) {
+  const unsigned long long at = t.base + (unsigned)q;
+  if (q >= t.k) return 2;
+  if (at >= t.capacity) return 1;
+  const unsigned act = (unsigned)w & 0xFFu;
+  const double aux = act == MJP_ACT_AJ ? t.aj_ends : (act == MJP_ACT_EJ ? t.ej_ent : __longlong_as_double(0x7FF8000000000000ll));
+  const unsigned long long w2 = (unsigned long long)(uint32_t)(w >> 32) | ((unsigned long long)t.inst << 32);
+  const unsigned long long w3 = (unsigned long long)(t.line_cnt + (uint32_t)q) | (((w >> 16) & 0x7FFFull) << 32) |
+                                ((w & 0xFFull) << 48) | (((w >> 8) & 0xFFull) << 56);
+  // two 16-byte streaming stores = one full 32-byte sector per record, not kept in L2
+  double2 *dst = reinterpret_cast<double2 *>(t.out + at);
+  __stcs(dst, make_double2(t.clk, aux));
+  __stcs(dst + 1, make_double2(__longlong_as_double((long long)w2), __longlong_as_double((long long)w3)));
+  return 0;
+}
+// clean-log-buf in general (util/log.clj:38-57): machines in order of first appearance (group-by :m), within a
+// machine the classes in order of first appearance, within a class the original order; a machine's :bl/:ub
+// (:st/:us) are dropped iff exactly two (masks two_b / two_s).  Out of line: ticks that are not already in
+// this order are the exception.  Returns records written | dropped << 16 | mismatch << 31.
+template <typename MaskT>
+__device__ __noinline__ unsigned emit_general(const LogTick t, const unsigned long long *stage, int ns, MaskT two_b,
+                                              MaskT two_s) {
+  unsigned q = 0, dropped = 0, bad = 0;
+  MaskT done_m = 0;                                          // machines whose group has been written
+  for (int a = 0; a < ns; ++a) {
+    const unsigned m = (unsigned)(stage[a] >> 8) & 0xFFu;
+    const MaskT mbit = (MaskT)1 << m;
+    if (done_m & mbit) continue;
+    done_m |= mbit;
+    uint32_t order = 0;                                      // classes of machine m in order of first appearance
+    int no = 0;
+    unsigned have = 0;
+    for (int b = a; b < ns; ++b) {
+      const unsigned wb = (unsigned)stage[b];
+      if (((wb >> 8) & 0xFFu) != m) continue;
+      const unsigned c = log_class(wb & 0xFFu);
+      if (!((have >> c) & 1u)) { have |= 1u << c; order |= c << (2 * no); ++no; }
+    }
+    for (int r = 0; r < no; ++r) {
+      const unsigned c = (order >> (2 * r)) & 3u;
+      if ((c == 0u && (two_b & mbit)) || (c == 1u && (two_s & mbit))) continue;         // util/log.clj:51-53
+      for (int b = a; b < ns; ++b) {
+        const unsigned long long w = stage[b];
+        if (((unsigned)(w >> 8) & 0xFFu) != m || log_class((unsigned)w & 0xFFu) != c) continue;
+        const int rc = put_record(t, (int)q, w);
+        dropped += rc == 1; bad |= rc == 2;
+        ++q;
+      }
+    }
+  }
+  return (q & 0xFFFFu) | ((dropped & 0x7FFFu) << 16) | (bad << 31);
+}
 
 // end-time (core.clj:138-151) split at the points where it needs an event that may not exist yet.
 // begin: at job start.  `machine_up`: :future is a :down event at fut_t.  Returns true when the job
@@ -372,12 +439,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) return k;
     return -1;
   };
-  // ---- SCADA capture (LOG): :log-buf of the current tick, staged in shared memory ----
-  // word: act | m << 8 | n << 16 | done << 31 | job << 32
-  unsigned long long *s_stage =
-      reinterpret_cast<unsigned long long *>(sf + (size_t)(hb + 3 + (MT > 0 ? 0 : M)) * nt);
-  // cleaned order, 4 indices per word: after the hot u32 slots (and the cold ones when they share the array)
-  uint32_t *s_ord = su + (size_t)(COLD ? M - 1 : 3 * M - 1 + jtw + (REPLAY ? M : 0)) * nt;
+  // ---- SCADA capture (LOG): :log-buf of the current tick, staged in an L2-resident scratch ----
+  // [instance][slot]: the messages of an instance share cache lines with nobody else, so after the first
+  // load of a tick the cleaning loops below run out of L1; rows beyond a tick's few messages are never
+  // touched.  The capture costs no shared memory (same residency as a stats-only run).
+  // word: act | m << 8 | n << 16 | job << 32
+  unsigned long long *g_stage = LOG ? p.stage + (size_t)g * (size_t)p.stage_cap : nullptr;
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
   uint32_t line_cnt = 0;                                   // [:report :line-cnt]
@@ -387,76 +454,64 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     // :max-lines has been reached is never printed, so there is nothing to stage for it
     if (clock < p.warm_up || (uint64_t)line_cnt >= p.max_lines) return;
     if (n_staged < stage_cap)
-      s_stage[n_staged * nt] = (unsigned long long)act | ((unsigned long long)m << 8) |
-                               ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);
+      g_stage[n_staged] = (unsigned long long)act | ((unsigned long long)m << 8) |
+                          ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);
     else flags |= F_OVF;
     n_staged++;
   };
-  // clean-log-buf (util/log.clj:38-57) + print-lines (util/log.clj:111-137): order the staged messages,
-  // reserve space with ONE atomicAdd per warp, write 32-byte records.
+  // clean-log-buf (util/log.clj:38-57) + print-lines (util/log.clj:111-137).  The number of messages that
+  // survive cleaning follows from the tick masks (a machine's :bl/:ub or :st/:us messages are dropped iff
+  // there are exactly two, util/log.clj:51-53), so space is reserved first -- ONE atomicAdd per warp -- and
+  // the 32-byte records are written while the cleaned order is being discovered: machines in order of first
+  // appearance (group-by :m, util/log.clj:44), within a machine the classes {:bl :ub}, {:st :us}, rest in
+  // order of first appearance, within a class the original order.
   auto emit_tick = [&](const unsigned fm, const double tick_clk) {
     const int lane = tid & 31;
     const double ej_ent = EJENT;
-    const int ns = n_staged < stage_cap ? n_staged : stage_cap;
     const bool print_now = p.log_on && tick_clk >= p.warm_up && p.max_lines > (uint64_t)line_cnt;   // util/log.clj:220-226
-    int k = 0;
-    if (print_now) {
-      for (int a = 0; a < ns; ++a) {
-        const unsigned long long wa = s_stage[a * nt];
-        if (wa & (1ull << 31)) continue;
-        const int m = (int)((wa >> 8) & 0xFF);                 // next machine in (group-by :m) order
-        int cnt[3] = {0, 0, 0}, order[3], no = 0;
-        for (int b = a; b < ns; ++b) {
-          const unsigned long long wb = s_stage[b * nt];
-          if ((int)((wb >> 8) & 0xFF) != m) continue;
-          const int act = (int)(wb & 0xFF);
-          const int c = (act == MJP_ACT_BL || act == MJP_ACT_UB) ? 0 : ((act == MJP_ACT_ST || act == MJP_ACT_US) ? 1 : 2);
-          if (cnt[c]++ == 0) order[no++] = c;
-        }
-        for (int q = 0; q < no; ++q) {
-          const int c = order[q];
-          const bool drop = (c < 2) && cnt[c] == 2;            // util/log.clj:51-53
-          for (int b = a; b < ns; ++b) {
-            const unsigned long long wb = s_stage[b * nt];
-            if ((int)((wb >> 8) & 0xFF) != m) continue;
-            const int act = (int)(wb & 0xFF);
-            const int cc = (act == MJP_ACT_BL || act == MJP_ACT_UB) ? 0 : ((act == MJP_ACT_ST || act == MJP_ACT_US) ? 1 : 2);
-            if (cc != c) continue;
-            s_stage[b * nt] = wb | (1ull << 31);
-            if (!drop) { setb(s_ord, (size_t)nt, k, (uint32_t)b); ++k; }
-          }
-        }
-      }
-    }
-    // warp-aggregated reservation over the lanes that flush in this micro-step
+    const int ns = (print_now && !(flags & F_OVF)) ? n_staged : 0;
+    const int k = ns ? ns - 2 * (MO::popc(twoB) + MO::popc(twoS)) : 0;
+    // warp-aggregated reservation over the lanes that flush in this micro-step: bit-sliced prefix sum of k
     unsigned prefix = 0, total = 0;
-    for (unsigned rest = fm; rest;) {
-      const int src = __ffs((int)rest) - 1; rest &= rest - 1;
-      const unsigned v = __shfl_sync(fm, (unsigned)k, src);
-      if (src < lane) prefix += v;
-      total += v;
+    const unsigned below = (1u << lane) - 1u;
+    for (int bit = 0; __any_sync(fm, ((unsigned)k >> bit) != 0); ++bit) {
+      const unsigned bal = __ballot_sync(fm, ((unsigned)k >> bit) & 1u);
+      prefix += (unsigned)__popc(bal & below) << bit;
+      total += (unsigned)__popc(bal) << bit;
     }
     unsigned long long base = 0;
     const int leader = __ffs((int)fm) - 1;
     if (lane == leader && total) base = atomicAdd(p.log_cursor, (unsigned long long)total);
-    base = __shfl_sync(fm, base, leader);
-    if (k) {
-      mjp_log_record *out = reinterpret_cast<mjp_log_record *>(p.log_records);
-      unsigned dropped = 0;
-      for (int q = 0; q < k; ++q) {
-        const unsigned long long w = s_stage[getb(s_ord, (size_t)nt, q) * nt];
-        const unsigned long long at = base + prefix + q;
-        if (at >= p.log_capacity) { ++dropped; continue; }
-        const int act = (int)(w & 0xFF);
-        const double aux = act == MJP_ACT_AJ ? aj_ends : (act == MJP_ACT_EJ ? ej_ent : QNAN);
-        // two 16-byte stores = one full 32-byte sector per record
-        const unsigned long long w2 = (unsigned long long)(uint32_t)(w >> 32) | ((unsigned long long)(uint32_t)g << 32);
-        const unsigned long long w3 = (unsigned long long)(line_cnt + q) | (((w >> 16) & 0x7FFFull) << 32) |
-                                      ((w & 0xFFull) << 48) | (((w >> 8) & 0xFFull) << 56);
-        double2 *dst = reinterpret_cast<double2 *>(out + at);
-        dst[0] = make_double2(tick_clk, aux);
-        dst[1] = make_double2(__longlong_as_double((long long)w2), __longlong_as_double((long long)w3));
-      }
+    base = __shfl_sync(fm, base, leader) + prefix;
+    const LogTick lt{reinterpret_cast<mjp_log_record *>(p.log_records), base, p.log_capacity, tick_clk, aj_ends, ej_ent,
+                     line_cnt, (uint32_t)g, k};
+    unsigned dropped = 0;
+    int q = 0;
+    // Nearly every tick is grouped already (each machine's messages adjacent, each class within them adjacent):
+    // then cleaning keeps the original order and ONE voted pass writes the records.  The pass notices when a
+    // tick is not grouped; that tick is then written again by the general, out-of-line routine (same k, same
+    // slots).
+    MaskT gdone = 0;
+    unsigned cdone = 0, pm = 0xFFFFFFFFu, pc = 3u;
+    bool grouped = true;
+    for (int x = 0; __any_sync(fm, x < ns); ++x) if (x < ns) {
+      const unsigned long long w = g_stage[x];
+      const unsigned act = (unsigned)w & 0xFFu, m = (unsigned)(w >> 8) & 0xFFu, c = log_class(act);
+      const MaskT mbit = MJP_BIT(m);
+      if (m != pm) { if (gdone & mbit) grouped = false; gdone |= mbit; cdone = 0u; pm = m; pc = 3u; }
+      if (c != pc) { if ((cdone >> c) & 1u) grouped = false; cdone |= 1u << c; pc = c; }
+      if ((c == 0u && (twoB & mbit)) || (c == 1u && (twoS & mbit))) continue;           // util/log.clj:51-53
+      const int r = put_record(lt, q, w);
+      dropped += r == 1; if (r == 2) flags |= F_OVF;
+      ++q;
+    }
+    if (!grouped) {
+      const unsigned r = emit_general<MaskT>(lt, g_stage, ns, twoB, twoS);
+      q = (int)(r & 0xFFFFu); dropped = (r >> 16) & 0x7FFFu;
+      if (r >> 31) flags |= F_OVF;
+    }
+    if (ns) {
+      if (q != k) flags |= F_OVF;
       if (dropped) atomicAdd(p.log_cursor + 1, (unsigned long long)dropped);
       line_cnt += (uint32_t)k;                               // util/log.clj:137
     }

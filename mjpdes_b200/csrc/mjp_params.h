@@ -43,6 +43,7 @@ struct KParams {
   void *log_records;      // mjp_log_record[log_capacity]
   uint64_t log_capacity;
   unsigned long long *log_cursor;   // [0] next free record, [1] records dropped
+  unsigned long long *stage;        // LOG mode: [n_inst][stage_cap] messages of the current tick (global scratch)
   // shared-memory layout
   int32_t nf64, nu32;     // per-thread slots
   int32_t const_bytes;    // CTA constant table size (multiple of 16)

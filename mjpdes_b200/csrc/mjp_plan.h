@@ -29,9 +29,10 @@ inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Per-thread shared-memory slots of one kernel variant (must mirror the macros in mjp_line_kernel.cuh):
 //   cold f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1]         cold u32: FUT_N[M] STARTED[M] JT[R/4] EIDX[M] if REPLAY
-//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] unless in registers | stage[stage_cap] if LOG
-//   hot  u32: CNT[M-1] | ORD[stage_cap/4] if LOG
-// Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX ORD);
+//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] unless in registers
+//   hot  u32: CNT[M-1]
+// SCADA capture (LOG) stages a tick's messages in a global scratch of stage_cap words per instance, not here.
+// Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX);
 // with it they live in a global scratch of cold_f64_slots / cold_u32_slots rows per instance.
 inline int cold_f64_slots(const KParams &kp) { return 5 * kp.M - 1; }
 inline int cold_u32_slots(const KParams &kp, bool replay) {
@@ -39,8 +40,9 @@ inline int cold_u32_slots(const KParams &kp, bool replay) {
 }
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
-  kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : M) + (log ? kp.stage_cap : 0);
-  kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1) + (log ? ((kp.stage_cap + 3) >> 2) : 0);
+  (void)log;
+  kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : M);
+  kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1);
   return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
 }
 
@@ -74,10 +76,9 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   }
   kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
   // SCADA capture stages one tick of messages per instance.  A machine logs at most nine messages in a tick
-  // (complete, start, :bl, :ub, :st, :us, :up, :down and a re-fired :up/:down); the cleaned-order list holds
-  // one byte per message, hence the cap of 255 (beyond it: MJP_INST_TICK_OVERFLOW, lines of >= 28 machines
-  // on which nearly every machine acts at the same instant).
-  kp.stage_cap = L->log ? (9 * M + 4 < 255 ? 9 * M + 4 : 255) : 0;
+  // (complete, start, :bl, :ub, :st, :us, :up, :down and a re-fired :up/:down); beyond the cap the instance ends
+  // with MJP_INST_TICK_OVERFLOW.  The stage is a global scratch whose unused rows are never touched.
+  kp.stage_cap = L->log ? (9 * M + 4 + 15) / 16 * 16 : 0;      // whole 128-byte lines per instance
   kp.refill_lanes = 8;
   pl.per_thread_bytes = plan_layout(kp, false, true, L->log != 0);   // the largest variant
   return pl;

@@ -134,6 +134,12 @@ class Handle:
         return RunResult(self._line, stats, hlog.view().copy() if hlog else None, rc, self.kernel_ms(),
                          self.launch_count())
 
+    def log_count(self) -> tuple[int, int]:
+        """(records captured, records dropped) by the last launch, without copying the records to the host."""
+        lo = abi.LogOut(None, (1 << 62), 0, 0)
+        self._check(self._lib.mjp_download(self._h, None, C.byref(lo)), allow=(abi.OK, abi.LOG_TRUNCATED))
+        return int(lo.count), int(lo.dropped)
+
     def download_fields(self, names) -> abi.HostStats:
         """Copy back only the named planes of the last launch (e.g. ("n_events", "aggregate"))."""
         stats = abi.HostStats(self._line, self._n)

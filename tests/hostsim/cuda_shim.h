@@ -51,5 +51,6 @@ static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline void __stcs(double2 *p, double2 v) { *p = v; }
 #define __maxnreg__(...)
 #define __noinline__

@@ -33,7 +33,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   for (size_t q = 0; q < (size_t)kp.L * n_inst; ++q) s->occ_time[q] = 0;
   for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; s->n_events[q] = 0; }
   const bool cold = force_cold != 0;
-  const bool mt_ok = !cold && !want_log_early && M >= 2 && M <= 8;
+  const bool mt_ok = !cold && M >= 2 && M <= 8;
   mjp::plan_layout(kp, mt_ok, rng->mode != MJP_RNG_COUNTER, want_log_early, cold);
   std::vector<double> coldf((size_t)mjp::cold_f64_slots(kp) * n_inst);
   std::vector<uint32_t> coldu((size_t)mjp::cold_u32_slots(kp, true) * n_inst);
@@ -45,7 +45,8 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   const bool replay = rng->mode != MJP_RNG_COUNTER, hash = want_hash != 0;
   unsigned long long cursor[2] = {0, 0};
   const bool want_log = log && L->log;
-  if (want_log) { kp.log_records = log->records; kp.log_capacity = log->capacity; kp.log_cursor = cursor; }
+  std::vector<unsigned long long> stage(want_log ? (size_t)kp.stage_cap * n_inst : 0);
+  if (want_log) { kp.log_records = log->records; kp.log_capacity = log->capacity; kp.log_cursor = cursor; kp.stage = stage.data(); }
   kp.park_words = 72 + 2 * kp.nf64 + kp.nu32;
   std::vector<uint32_t> park((size_t)kp.park_words * n_inst);
   kp.park = park.data();
@@ -79,16 +80,11 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
       else { if (want_log) { RUNC(uint32_t, true) } else { RUNC(uint32_t, false) } }
     }
     else if (M > 32) { if (want_log) { RUN3(uint64_t, 0, true) } else { RUN3(uint64_t, 0, false) } }
-    else if (want_log) { RUN3(uint32_t, 0, true) }
     else switch (M) {
-      case 2: RUN3(uint32_t, 2, false) break;
-      case 3: RUN3(uint32_t, 3, false) break;
-      case 4: RUN3(uint32_t, 4, false) break;
-      case 5: RUN3(uint32_t, 5, false) break;
-      case 6: RUN3(uint32_t, 6, false) break;
-      case 7: RUN3(uint32_t, 7, false) break;
-      case 8: RUN3(uint32_t, 8, false) break;
-      default: RUN3(uint32_t, 0, false) break;
+#define RUNM(MT) case MT: if (want_log) { RUN3(uint32_t, MT, true) } else { RUN3(uint32_t, MT, false) } break;
+      RUNM(2) RUNM(3) RUNM(4) RUNM(5) RUNM(6) RUNM(7) RUNM(8)
+#undef RUNM
+      default: if (want_log) { RUN3(uint32_t, 0, true) } else { RUN3(uint32_t, 0, false) } break;
     }
   }
   }
