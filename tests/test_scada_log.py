@@ -109,6 +109,25 @@ def test_gpu_log_truncation_is_reported_not_overrun(engine, oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_log_count_without_copy_and_no_hash_variants(oracle):
+    """The capture variants an un-instrumented handle launches (no event hash; register-resident :ends for
+    M <= 8, generic above), and Handle.log_count(): the record count without moving the stream to the host."""
+    from mjpdes_b200 import engine as E
+    with E.Handle(device=0) as h:
+        for line, n in ((example_line(run_to=900, warm_up=100, log=True, up_down=True, max_lines=abi.UINT64_MAX), 333),
+                        (mixed20_line(warm_up=20, run_to=200), 70)):
+            want = oracle.run(line, n, seed=SEED, log_capacity=3_000_000, n_threads=8)
+            h.upload(line, n)
+            h.reserve_log(3_000_000)
+            h.launch(abi.RNG_COUNTER, SEED, 0, want_log=True)
+            h.sync()
+            assert h.log_count() == (len(want.log), 0)
+            got = h.download(log_capacity=3_000_000)
+            assert_same_log(got.log, want.log)
+            assert np.array_equal(got.stats.blocked_time, want.stats.blocked_time)
+
+
+@pytest.mark.gpu
 def test_gpu_c4_shape_log_volume(engine):
     """C4 (20 machines, mixed BAS/BBS, 8 job types, SCADA on): record count per instance is what the
     executed actions imply; every instance's lines are 0..k-1 with non-decreasing clocks."""
