@@ -533,7 +533,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       if (open0 && t0 == t0) red_add((is_s ? p.starved : p.blocked) + (size_t)i * n_inst + g, tick_clk - t0);
       *slot = open1 ? tick_clk : QNAN;
     };
-    if (sizeof(MaskT) == 4) {
+    if (MT > 0) {                                             // M <= 8: both masks fit one 32-bit word
+      uint32_t q = warm ? ((uint32_t)pB | ((uint32_t)pS << 16)) : 0u;
+      while (__any_sync(fm, q != 0)) if (q) {
+        const int j = __ffs((int)q) - 1; q &= q - 1;
+        interval(j & 15, j >= 16);
+      }
+    } else if (sizeof(MaskT) == 4) {
       uint64_t q = warm ? ((uint64_t)pB | ((uint64_t)pS << 32)) : 0ull;
       while (__any_sync(fm, q != 0)) if (q) {
         const int j = __ffsll((long long)q) - 1; q &= q - 1;
