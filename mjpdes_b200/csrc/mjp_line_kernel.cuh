@@ -404,7 +404,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   if (REPLAY && fresh_start)
     for (int i = 0; i < M; ++i) if (!(FUT_T(i) == FUT_T(i))) flags |= F_TAPE;   // a tape too short for the first event
 
-  int type_cache = -2;                 // job type of the NEXT job when already drawn (-2: not drawn)
+  // Job types drawn ahead of the jobs that will use them: bits 0-23 hold up to three types (0xFF = nil) for
+  // jobs curjob+1.., bits 24.. their count.  A Philox block yields the types of two consecutive jobs, and the
+  // draw runs for every lane of the warp that is down to <= 1 whenever ONE lane has none left (a draw per
+  // lane-in-need was 92 % of the warp's Philox executions at 1.7 active lanes).  Which block a job uses
+  // depends on its number only, so drawing early changes nothing observable.
+  uint32_t tq = 0;
+  const bool jt_random = !(K == 1 && c_thr[0] >= 1.0) && !(REPLAY && p.tape_jt != nullptr);
 
   auto mark_seen = [&](int i) {       // (group-by :m) order, util/log.clj:44 -- branch-free
     const MaskT bit = MJP_BIT(i);
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   D(clock)                                                                                                  \
   MK(up) MK(occ) MK(B) MK(S) MK(full) MK(empty) MK(pend) MK(dup) MK(fired) MK(need)                         \
   MK(seen) MK(lead) MK(touched) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc)                \
-  U(curjob) U(n_ev) U(flags) U(type_cache)   /* (flags is parked before the :status code is put into it) */
+  U(curjob) U(n_ev) U(flags) U(tq)   /* (flags is parked before the :status code is put into it) */
   // state that exists only in some variants (parking it unconditionally would keep it alive everywhere)
 #define MJP_PARK_LOG(D, U) D(aj_ends) U(line_cnt) U(n_staged)
   auto park_save = [&]() {
@@ -653,6 +659,18 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       finish(MJP_INST_NORMAL_END); live = false;
     } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
     else if (SLICE && clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
+
+    // new-job core.clj:328-340: keep at least one drawn job type per lane (see tq); here, before the guards,
+    // few values are live across the out-of-line call
+    if (jt_random && __any_sync(am, live && (tq >> 24) == 0u)) {
+      const uint32_t cnt = tq >> 24;
+      if (live && cnt <= 1u) {
+        double u0, u1;
+        jobtype_uniforms((curjob + cnt) >> 1, p.first_id + g, p.seed, &u0, &u1);   // curjob + cnt is even
+        const uint32_t t0 = (uint32_t)type_from(u0) & 0xFFu, t1 = (uint32_t)type_from(u1) & 0xFFu;
+        tq = (tq & ((1u << (8u * cnt)) - 1u)) | (t0 << (8u * cnt)) | (t1 << (8u * cnt + 8u)) | ((cnt + 2u) << 24);
+      }
+    }
 
     // ---- runables (core.clj:515-531): guards on the pre-batch state ----
     const MaskT notfull = ~full, nonempty = ~empty;
@@ -723,21 +741,15 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 
     // ---- run the batch in generator order, core.clj:742 ----
     if (__any_sync(am, b_aj != 0)) {
-      if (b_aj) {                                            // add-job core.clj:240-254, new-job core.clj:328-340
+      if (b_aj) {                                            // add-job core.clj:240-254
         int type;
-        if (K == 1 && c_thr[0] >= 1.0) type = 0;
-        else if (type_cache != -2) { type = type_cache; type_cache = -2; }
-        else {
-          if (REPLAY && p.tape_jt != nullptr) {             // MJP_RNG_TAPE: rand of new-job, core.clj:331
-            if (curjob < p.tape_len_jt) type = type_from(p.tape_jt[(size_t)g * p.tape_len_jt + curjob]);
-            else { type = -1; flags |= F_TAPE; }
-          } else {
-            double u0, u1;
-            jobtype_uniforms(curjob >> 1, p.first_id + g, p.seed, &u0, &u1);
-            if (curjob & 1) type = type_from(u1);
-            else { type = type_from(u0); type_cache = type_from(u1); }
-          }
-        }
+        if (jt_random) {
+          type = (int)(tq & 0xFFu);
+          if (type == 0xFF) type = -1;
+          tq = ((tq >> 8) & 0xFFFFu) | (((tq >> 24) - 1u) << 24);
+        } else if (!(REPLAY && p.tape_jt != nullptr)) type = 0;
+        else if (curjob < p.tape_len_jt) type = type_from(p.tape_jt[(size_t)g * p.tape_len_jt + curjob]);   // MJP_RNG_TAPE: rand of new-job, core.clj:331
+        else { type = -1; flags |= F_TAPE; }
         if (type < 0) {                                      // the reference dies in job-requires
           finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED : MJP_INST_JOBTYPE_NIL); live = false;
           b_ud = b_tb = b_tm = b_st = b_us = b_bl = b_ub = 0;
