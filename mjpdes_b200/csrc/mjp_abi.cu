@@ -416,7 +416,6 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     const int blocks = (int)((kp.n_inst + threads - 1) / threads);
     const bool slice = resume || until < std::numeric_limits<double>::infinity();
     mjp::KParams kl = kp;                         // tapes are read by MJP_RNG_TAPE launches only
-    if (const char *rl = std::getenv("MJP_REFILL_LANES")) kl.refill_lanes = std::atoi(rl);   // tuning experiments
     if (rng->mode != MJP_RNG_TAPE) kl.tape_jt = kl.tape_u = kl.tape_e = nullptr;
     cudaError_t e = launch_line_kernel(replay, hash, slice, h->want_log, cold, kl, blocks, threads, h->smem_bytes, h->stream);
     CK(e);

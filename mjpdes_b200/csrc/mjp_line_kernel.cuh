@@ -21,9 +21,10 @@
 //    resolved when the machine's next :up event fires -- the same f64 operations in
 //    the same order as core.clj:145-151, so :ends is bit-identical, and every
 //    up/down event is generated exactly once;
-//  * the NEXT up/down event of a machine is pre-generated lazily, out of line, when at
-//    least 8 lanes of the warp have one to generate (Philox + ln is ~200 instructions
-//    that only ~5 % of the events need);
+//  * random draws are made for the whole warp at once (Philox + ln is ~200 instructions
+//    that only ~5 % of the events need): the NEXT up/down event of a machine is generated,
+//    out of line, for every lane that lacks one when the first lane cannot wait any longer,
+//    and job types are drawn two jobs ahead for every lane that is down to one;
 //  * a clock tick's messages are not stored: what clean-log-buf + add-compute-log!
 //    would do with them is a function of (machines seen, in which order; parity of
 //    :bl/:ub and :st/:us per machine -- a pair cancels; which buffers got a :bj / :sm),
@@ -792,6 +793,23 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         }
       }
     }
+    {
+      // Pre-generate the event AFTER each machine's pending one (core.clj:180-191), lazily: the Philox + ln
+      // path is ~200 instructions and only ~5 % of the events need it, so it waits until one lane of the warp
+      // cannot wait any longer -- its pending event fires in this micro-step -- and then runs for every lane
+      // that has something to generate.
+      const MaskT need_l = live ? need : (MaskT)0;           // (a lane that has just parked or ended touches nothing)
+      if (__any_sync(am, (b_ud & need_l & ~dup) != 0)) {
+        for (MaskT q = need_l; __any_sync(am, q != 0);) if (q) {
+          const int i = MO::ffs(q); q &= q - 1;
+          const bool pending_is_up = !((up ^ dup) & MJP_BIT(i));
+          uint32_t ecur = REPLAY ? s_eidx[i * cs] : 0u;
+          NXT_T(i) = next_event_time(i, FUT_N(i), pending_is_up, FUT_T(i), ecur);
+          if (REPLAY) s_eidx[i * cs] = ecur;
+        }
+        if (live) need = 0;
+      }
+    }
     {                                                        // bring-machine-up, then -down: core.clj:215-238
       MaskT q_up = b_ud & ~up, q_dn = b_ud & up;
       while (__any_sync(am, (q_up | q_dn) != 0)) if (q_up | q_dn) {
@@ -812,12 +830,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         else {
           const double t_fire = FUT_T(i);
           const uint32_t n = FUT_N(i);
-          double t_next;
-          if (need & bit) {                                  // not pre-generated yet: do it here (rare)
-            uint32_t ecur = REPLAY ? s_eidx[i * cs] : 0u;
-            t_next = next_event_time(i, n, was_up_event, t_fire, ecur);
-            if (REPLAY) s_eidx[i * cs] = ecur;
-          } else t_next = NXT_T(i);
+          const double t_next = NXT_T(i);                  // generated above at the latest
           if (REPLAY && !(t_next == t_next)) flags |= F_TAPE;
           need |= bit;
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
@@ -828,23 +841,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
           }
           rescan_fut();
         }
-      }
-    }
-    {
-      // Pre-generate the event AFTER each machine's pending one (core.clj:180-191), lazily: the Philox + ln
-      // path is ~200 instructions and only ~5 % of the events need it, so it runs when at least 8 lanes of
-      // the warp have something to generate (or every active lane has), not whenever one lane does.
-      const MaskT need_l = live ? need : (MaskT)0;           // (a lane that has just parked or ended touches nothing)
-      const unsigned needm = __ballot_sync(am, need_l != 0);
-      if (__popc(needm) >= p.refill_lanes || needm == am) {
-        for (MaskT q = need_l; __any_sync(am, q != 0);) if (q) {
-          const int i = MO::ffs(q); q &= q - 1;
-          const bool pending_is_up = !((up ^ dup) & MJP_BIT(i));
-          uint32_t ecur = REPLAY ? s_eidx[i * cs] : 0u;
-          NXT_T(i) = next_event_time(i, FUT_N(i), pending_is_up, FUT_T(i), ecur);
-          if (REPLAY) s_eidx[i * cs] = ecur;
-        }
-        if (live) need = 0;
       }
     }
     for (MaskT q = b_tb; __any_sync(am, q != 0);) if (q) {   // advance2buffer core.clj:285-300

@@ -48,7 +48,6 @@ struct KParams {
   int32_t nf64, nu32;     // per-thread slots
   int32_t const_bytes;    // CTA constant table size (multiple of 16)
   int32_t stage_cap;      // LOG mode: messages staged per tick per instance
-  int32_t refill_lanes;   // lazy up/down generation runs when this many lanes of a warp need it
 };
 
 }  // namespace mjp

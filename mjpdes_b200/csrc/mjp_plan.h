@@ -79,7 +79,6 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   // (complete, start, :bl, :ub, :st, :us, :up, :down and a re-fired :up/:down); beyond the cap the instance ends
   // with MJP_INST_TICK_OVERFLOW.  The stage is a global scratch whose unused rows are never touched.
   kp.stage_cap = L->log ? (9 * M + 4 + 15) / 16 * 16 : 0;      // whole 128-byte lines per instance
-  kp.refill_lanes = 8;
   pl.per_thread_bytes = plan_layout(kp, false, true, L->log != 0);   // the largest variant
   return pl;
 }
