@@ -38,6 +38,8 @@ def main():
                ("next_event_time", find("auto next_event_time"), find("// ---- preprocess-model")),
                ("rescan_fut", find("auto rescan_fut"), find("if (fresh_start) rescan_fut();")),
                ("mark_seen/toggle/type_from", find("auto mark_seen"), find("// ---- SCADA capture")),
+               ("job-type draw (whole warp)", find("keep at least one drawn job type"), find("// ---- runables")),
+               ("up/down generation (whole warp)", find("Pre-generate the event AFTER"), find("bring-machine-up, then -down")),
                ("out-of-line generators", find("sojourn_counter(uint32_t idx"), find("#define MJP_BIT"))]
     agg = {}
     for r, loc in zip(inst, lm):
