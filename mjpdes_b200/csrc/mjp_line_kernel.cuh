@@ -472,10 +472,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // the 32-byte records are written while the cleaned order is being discovered: machines in order of first
   // appearance (group-by :m, util/log.clj:44), within a machine the classes {:bl :ub}, {:st :us}, rest in
   // order of first appearance, within a class the original order.
-  auto emit_tick = [&](const unsigned fm, const double tick_clk) {
+  auto emit_tick = [&](const bool on, const double tick_clk) {
+    constexpr unsigned fm = 0xffffffffu;
     const int lane = tid & 31;
     const double ej_ent = EJENT;
-    const bool print_now = p.log_on && tick_clk >= p.warm_up && p.max_lines > (uint64_t)line_cnt;   // util/log.clj:220-226
+    const bool print_now = on && p.log_on && tick_clk >= p.warm_up && p.max_lines > (uint64_t)line_cnt;   // util/log.clj:220-226
     const int ns = (print_now && !(flags & F_OVF)) ? n_staged : 0;
     const int k = ns ? ns - 2 * (MO::popc(twoB) + MO::popc(twoS)) : 0;
     // warp-aggregated reservation over the lanes that flush in this micro-step: bit-sliced prefix sum of k
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       total += (unsigned)__popc(bal) << bit;
     }
     unsigned long long base = 0;
-    const int leader = __ffs((int)fm) - 1;
+    const int leader = 0;
     if (lane == leader && total) base = atomicAdd(p.log_cursor, (unsigned long long)total);
     base = __shfl_sync(fm, base, leader) + prefix;
     const LogTick lt{reinterpret_cast<mjp_log_record *>(p.log_records), base, p.log_capacity, tick_clk, aj_ends, ej_ent,
@@ -522,13 +523,15 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       if (dropped) atomicAdd(p.log_cursor + 1, (unsigned long long)dropped);
       line_cnt += (uint32_t)k;                               // util/log.clj:137
     }
-    n_staged = 0;
+    if (on) n_staged = 0;
   };
   // push-log for the tick that just ended (util/log.clj:98-108): clean-log-buf + add-compute-log!.
-  // Entered by the lanes of `fm`; its three loops are voted over `fm` so the lanes stay together.
-  auto flush_tick = [&](const unsigned fm) {
+  // Entered by every lane of the warp (`on` = this lane has a tick to flush): its loops are voted over the
+  // full warp, lanes with nothing to flush bring empty lists.
+  auto flush_tick = [&](const bool on) {
+    constexpr unsigned fm = 0xffffffffu;
     const double tick_clk = TICKCLK;
-    const bool warm = tick_clk >= p.warm_up;                               // util/log.clj:104
+    const bool warm = on && tick_clk >= p.warm_up;                         // util/log.clj:104
     // :bl/:ub (and :st/:us) of a machine: dropped iff exactly two (util/log.clj:51-53); otherwise replayed
     // in order, which nets to: close the interval that was open at tick start (block- / starve-), then open
     // one iff the machine ends the tick blocked (starved).  Both kinds share one voted loop.
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
       LASTCLK(b) = tick_clk;
     }
-    if (flags & F_EJ) {
+    if (on && (flags & F_EJ)) {
       if (warm) {                                             // end-job util/log.clj:212-217
         red_add(p.residence + g, tick_clk - EJENT);
         atomicAdd(reinterpret_cast<unsigned long long *>(p.njobs) + g, 1ull);
@@ -575,10 +578,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev); n_ev = 0;
       }
     }
-    if (LOG) emit_tick(fm, tick_clk);
-    seen = lead = touched = 0;
-    pB = twoB = pS = twoS = 0;
-    flags &= ~(uint32_t)F_EJ;
+    if (LOG) emit_tick(on, tick_clk);
+    if (on) {
+      seen = lead = touched = 0;
+      pB = twoB = pS = twoS = 0;
+      flags &= ~(uint32_t)F_EJ;
+    }
   };
   // end-time at job start (core.clj:138-151), lazily: fits in the current up interval, or pending
   auto start_job = [&](int i, int type) {
@@ -647,19 +652,21 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 
   // ======================= main-loop-loop, core.clj:729-744 =======================
   // One micro-step per trip with the warp in lock-step.  Nothing leaves the body early: a lane that
-  // ends (or errs) empties its batch and rides along to the bottom, so every section can be a loop
-  // voted over `am` (__any_sync is the reconvergence point; ncu showed 3.9 of 32 lanes per
-  // instruction without it).
+  // ends (or errs, or lies past the end of the batch) empties its batch and rides along until the whole
+  // warp is done, so every section can be a loop voted over the FULL warp -- __any_sync is the
+  // reconvergence point (ncu showed 3.9 of 32 lanes per instruction without it), and with a constant
+  // full mask it is one VOTE instruction instead of four (REDUX + R2UR + BRA.DIV + VOTE, +8 %).
+  constexpr unsigned am = 0xffffffffu;
   for (;;) {
-    const unsigned am = __ballot_sync(0xffffffffu, active);
-    if (am == 0) break;
-    if (active) {
-    bool live = true;
+    if (!__any_sync(am, active)) break;
+    bool live = active;
     // end-main-loop? core.clj:722-727
-    if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
-      finish(MJP_INST_NORMAL_END); live = false;
-    } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
-    else if (SLICE && clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
+    if (active) {
+      if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
+        finish(MJP_INST_NORMAL_END); live = false;
+      } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
+      else if (SLICE && clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
+    }
 
     // new-job core.clj:328-340: keep at least one drawn job type per lane (see tq); here, before the guards,
     // few values are live across the out-of-line call
@@ -733,8 +740,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const bool will_log = live && (p.up_down ? true : ((b_aj | b_tb | b_tm | b_st | b_us | b_bl | b_ub) != 0));
     {
       const bool do_flush = will_log && seen != 0 && !(flags & F_TICK);   // push-log of the previous tick
-      const unsigned fm = __ballot_sync(am, do_flush);
-      if (do_flush) flush_tick(fm);
+      flush_tick(do_flush);
       if (will_log && !(flags & F_TICK)) { TICKCLK = clock; flags |= F_TICK; }
     }
     n_ev += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
@@ -906,7 +912,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     else if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW); live = false; }
     else if (live && seen == 0) { finish(MJP_INST_LOGBUF_EMPTY); live = false; }    // push-log returned nil, util/log.clj:95
     active = live;
-    }
   }
   if (!ran) return;
   atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
