@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // The instance ends with this :status.  Kept in bits 8.. of `flags` and stored once after the loop: the
   // rare paths that end an instance are if-converted, and a predicated global store at each of them was
   // ~30 issued instructions per micro-step.
-  auto finish = [&](int code) { flags = (flags & 0xFFu) | ((uint32_t)(code + 1) << 8); };
+  auto finish = [&](int code) { flags |= (uint32_t)(code + 1) << 8; };   // at most once per instance and launch
   if (REPLAY && fresh_start)
     for (int i = 0; i < M; ++i) if (!(FUT_T(i) == FUT_T(i))) flags |= F_TAPE;   // a tape too short for the first event
 
@@ -817,14 +817,23 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       }
     }
     {                                                        // bring-machine-up, then -down: core.clj:215-238
-      MaskT q_up = b_ud & ~up, q_dn = b_ud & up;
-      while (__any_sync(am, (q_up | q_dn) != 0)) if (q_up | q_dn) {
-        const bool from_up = q_up != 0;                      // (no reference-select: it would pin both masks in local memory)
-        const MaskT qq = from_up ? q_up : q_dn;
-        const MaskT bit = qq & (~qq + 1);
-        const int i = MO::ffs(qq);
-        q_up &= from_up ? ~bit : ~(MaskT)0;
-        q_dn &= from_up ? ~(MaskT)0 : ~bit;
+      // M <= 8: both masks are one 32-bit list (ups in bits 0-7, downs in bits 8-15)
+      uint32_t q32 = MT > 0 ? ((uint32_t)(b_ud & ~up) | ((uint32_t)(b_ud & up) << 8)) : 0u;
+      MaskT q_up = MT > 0 ? (MaskT)0 : (b_ud & ~up), q_dn = MT > 0 ? (MaskT)0 : (b_ud & up);
+      while (__any_sync(am, MT > 0 ? q32 != 0u : (q_up | q_dn) != 0)) if (MT > 0 ? q32 != 0u : (q_up | q_dn) != 0) {
+        int i;
+        MaskT bit;
+        if (MT > 0) {
+          const int j = __ffs((int)q32) - 1; q32 &= q32 - 1u;
+          i = j & 7; bit = MJP_BIT(i);
+        } else {
+          const bool from_up = q_up != 0;                    // (no reference-select: it would pin both masks in local memory)
+          const MaskT qq = from_up ? q_up : q_dn;
+          bit = qq & (~qq + 1);
+          i = MO::ffs(qq);
+          q_up &= from_up ? ~bit : ~(MaskT)0;
+          q_dn &= from_up ? ~(MaskT)0 : ~bit;
+        }
         const bool was_up_event = !(up & bit);
         if (HASH) {
           hmix(h, (uint64_t)(was_up_event ? MJP_ACT_UP : MJP_ACT_DOWN) | ((uint64_t)i << 8));
@@ -890,8 +899,21 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       occ |= bit; STARTED(i) = id;
       if (fired & bit) { dup |= bit; up ^= bit; }
     }
-    {                                                        // record-actions core.clj:304-326, in the order
-      MaskT q_st = b_st, q_us = b_us, q_bl = b_bl, q_ub = b_ub;   // new-starved, -unstarved, -blocked, -unblocked
+    if (MT > 0) {                                            // record-actions core.clj:304-326, in the order
+      // new-starved, -unstarved, -blocked, -unblocked; M <= 8: the four masks are one 32-bit list
+      uint32_t q = (uint32_t)b_st | ((uint32_t)b_us << 8) | ((uint32_t)b_bl << 16) | ((uint32_t)b_ub << 24);
+      while (__any_sync(am, q != 0)) if (q) {
+        const int j = __ffs((int)q) - 1; q &= q - 1;
+        const int which = j >> 3, i = j & 7;
+        const MaskT bit = MJP_BIT(i);
+        if (HASH) { hmix(h, (uint64_t)(MJP_ACT_ST + which) | ((uint64_t)i << 8)); hmix(h, d2bits(clock)); hmix(h, 0); }
+        mark_seen(i);
+        if (LOG) stage_msg(MJP_ACT_ST + which, i, 0, 0u);
+        if (which < 2) { S ^= bit; toggle(pS, twoS, bit); }
+        else { B ^= bit; toggle(pB, twoB, bit); }
+      }
+    } else {
+      MaskT q_st = b_st, q_us = b_us, q_bl = b_bl, q_ub = b_ub;
       while (__any_sync(am, (q_st | q_us | q_bl | q_ub) != 0)) if (q_st | q_us | q_bl | q_ub) {
         const int which = q_st ? 0 : (q_us ? 1 : (q_bl ? 2 : 3));
         const MaskT qq = which == 0 ? q_st : (which == 1 ? q_us : (which == 2 ? q_bl : q_ub));
