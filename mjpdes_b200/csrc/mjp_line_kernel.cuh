@@ -930,9 +930,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         else { B ^= bit; toggle(pB, twoB, bit); }
       }
     }
-    if (live && (flags & F_TAPE)) { finish(MJP_INST_TAPE_EXHAUSTED); live = false; }
-    else if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW); live = false; }
-    else if (live && seen == 0) { finish(MJP_INST_LOGBUF_EMPTY); live = false; }    // push-log returned nil, util/log.clj:95
+    if (live && ((flags & (F_TAPE | F_OVF)) != 0 || seen == 0)) {        // rare: one test on the common path
+      finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED
+                              : ((flags & F_OVF) ? MJP_INST_TICK_OVERFLOW
+                                                 : MJP_INST_LOGBUF_EMPTY));   // push-log returned nil, util/log.clj:95
+      live = false;
+    }
     active = live;
   }
   if (!ran) return;

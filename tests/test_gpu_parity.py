@@ -188,7 +188,7 @@ def test_c2_full_size_properties(engine):
     assert len(np.unique(s.event_hash)) == n              # every replication is a different realisation
 
 
-@pytest.mark.parametrize("M,K,n,run_to", [(50, 16, 12032, 100.0), (10, 1, 50048, 100.0)])
+@pytest.mark.parametrize("M,K,n,run_to", [(50, 16, 12001, 100.0), (10, 1, 50021, 100.0)])   # last warp partly idle
 def test_cold_layout_variants_on_device(engine, oracle, M, K, n, run_to):
     """Batches of wide lines that do not fit one wave with all state in shared memory switch to the COLD
     variants (cold per-instance state in an L2-resident scratch, mjp_abi.cu): same results bit for bit."""

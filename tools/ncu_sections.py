@@ -30,7 +30,7 @@ def main():
              ("AJ section", find("if (__any_sync(am, b_aj != 0))")), ("UP/DOWN section", find("bring-machine-up, then -down")),
              ("TOBUF section", find("// advance2buffer core.clj:285-300")), ("TOMACH section", find("// advance2machine core.clj:263-277")),
              ("record-actions section", find("record-actions core.clj:304-326, in the order")),
-             ("loop tail", find("if (live && (flags & F_OVF)) { finish(MJP_INST_TICK_OVERFLOW)"))]
+             ("loop tail", find("rare: one test on the common path"))]
     helpers = [("flush_tick", find("auto flush_tick"), find("auto start_job")),
                ("SCADA stage/emit", find("auto stage_msg"), find("// push-log for the tick that just ended")),
                ("byte get/set, params", find("auto getb"), find("double r_end[")),
