@@ -694,22 +694,34 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     // advance2buffer candidate is a "now" candidate; a BAS new-blocked candidate that is late has
     // :ends == clock (an occupied, unblocked BAS machine always owns a candidate at :ends, so the clock
     // cannot pass it).  Only the strictly-future :ends need a min.
-    MaskT late = 0;
-#pragma unroll
-    for (int i = 0; i < (MT > 0 ? MT : M); ++i)
-      if (clock >= (MT > 0 ? r_end[i] : ENDS_S(i))) late |= MJP_BIT(i);
-    late &= occ & ~pend;
-    const MaskT c_st = ~S & empty & (~occ | late) & ALL;       // finished? = no job or clock >= :ends   core.clj:451-460, utils.clj:68-74
-    const MaskT tb_now = c_tb & late, bl_now = c_bla & late, fut = (c_tb | c_bla) & ~late;
-    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup | tb_now | bl_now) != 0;
-
-    // min over the future candidates: pending up/down events (cached) and future :ends
+    // The same pass takes the min over the future candidates: pending up/down events (cached) and the
+    // strictly-future :ends of the machines that own an :ends candidate (c_tb | c_bla, all occupied and not pending).
+    const MaskT cand = c_tb | c_bla;
     const double tmin_ud = TMINUD;
     double tmin = tmin_ud;
+    MaskT late = 0;
+    if (MT > 0) {                                            // :ends in registers: the late mask first ...
 #pragma unroll
-    for (int i = 0; i < (MT > 0 ? MT : M); ++i) {
-      const double e = (fut & MJP_BIT(i)) ? (MT > 0 ? r_end[i] : ENDS_S(i)) : INF;
-      tmin = e < tmin ? e : tmin;
+      for (int i = 0; i < MT; ++i) if (clock >= r_end[i]) late |= MJP_BIT(i);
+    } else {                                                 // :ends in shared memory: one pass, one load each
+      for (int i = 0; i < M; ++i) {
+        const double e = ENDS_S(i);
+        const bool over = clock >= e;
+        if (over) late |= MJP_BIT(i);
+        const double ef = ((cand & MJP_BIT(i)) && !over) ? e : INF;
+        tmin = ef < tmin ? ef : tmin;
+      }
+    }
+    late &= occ & ~pend;
+    const MaskT c_st = ~S & empty & (~occ | late) & ALL;       // finished? = no job or clock >= :ends   core.clj:451-460, utils.clj:68-74
+    const MaskT tb_now = c_tb & late, bl_now = c_bla & late, fut = cand & ~late;
+    const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup | tb_now | bl_now) != 0;
+    if (MT > 0) {                                            // ... then the min (two short passes are cheaper here)
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double e = (fut & MJP_BIT(i)) ? r_end[i] : INF;
+        tmin = e < tmin ? e : tmin;
+      }
     }
     bool live2 = live;
     if (live && (now_any ? (tmin < clock) : (tmin == INF))) {
