@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define ENDS_S(i)  sf[(hb + 3 + (i)) * nt]      /* :status :ends, or remaining work (MT == 0 only) */
 #define FUT_N(i)   cup[(i) * cs]                 /* :future index                      */
 #define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
-#define CNT(b)     su[(hu + (b)) * nt]          /* bits 0-7 (count :holding) of buffer b; bits 8.. this tick's
-                                                   occupancy bookkeeping, see buffer_tick_bits            */
+#define CNT(b)     su[(hu + (b)) * nt]          /* bits 0-7 (count :holding) of buffer b; bits 8-18 this tick's
+                                                   occupancy bookkeeping, see buffer_tick_bits; bits 24-31 :N */
   uint32_t *s_jt = cup + (size_t)(COLD ? 2 * M : 3 * M - 1) * cs;  /* job type ring, 4 per word    */
   const int jtw = K > 1 ? (p.R >> 2) : 0;                         /* a single job type needs no ring */
   uint32_t *s_eidx = s_jt + (size_t)jtw * cs;                     /* REPLAY only: exponential cursor */
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     if (is_up) up |= MJP_BIT(i);
   }
   for (int b = 0; fresh_start && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
-  for (int b = 0; fresh_start && b < M - 1; ++b) CNT(b) = 0u;
+  for (int b = 0; fresh_start && b < M - 1; ++b) CNT(b) = (uint32_t)cap_of(b) << 24;   // :N <= 254 (mjp_upload)
   // min over the machines' pending up/down times and who attains it: changes only when one fires
   MaskT m_udc = 0;
   auto rescan_fut = [&]() {
@@ -414,10 +414,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   const bool jt_random = !(K == 1 && c_thr[0] >= 1.0) && !(REPLAY && p.tape_jt != nullptr);
 
   auto mark_seen = [&](int i) {       // (group-by :m) order, util/log.clj:44 -- branch-free
+    // lead bit i: machine i's first message of the tick came before machine i+1's (both masks are zero
+    // at tick start and a machine is fresh once per tick, so the bit only ever needs setting)
     const MaskT bit = MJP_BIT(i);
-    const MaskT fresh = bit & ~seen;                          // first message of machine i in this tick?
-    const MaskT next_seen = (MaskT)0 - (((seen >> 1) >> i) & 1);   // all-ones iff machine i+1 logged already
-    lead = (lead & ~fresh) | (fresh & ~next_seen);
+    lead |= bit & ~seen & ~(seen >> 1);
     seen |= bit;
   };
   // buf+ / buf- (util/log.clj:159-171): of the messages a tick puts on a buffer, the FIRST IN CLEANED ORDER
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   auto buffer_tick_bits = [&](uint32_t w, MaskT bbit, int n, bool is_bj, bool precedes) -> uint32_t {
     if (!(touched & bbit)) {
       touched |= bbit;
-      return ((uint32_t)n << 8) | (is_bj ? 0x10000u : 0u) | 0x20000u;
+      return (w & 0xFF000000u) | ((uint32_t)n << 8) | (is_bj ? 0x10000u : 0u) | 0x20000u;
     }
     uint32_t hi = w & 0xFFFFFF00u;
     if ((((hi >> 16) & 1u) != 0) == is_bj || (hi & 0x40000u)) flags |= F_OVF;   // same kind twice, or a third message
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
         CNT(i) = (uint32_t)(n + 1) | buffer_tick_bits(cw, bit, n, true, ((lead >> i) & 1) != 0);
-        if (n + 1 == cap_of(i)) full |= bit;
+        if (n + 1 == (int)(cw >> 24)) full |= bit;
         empty &= ~(bit << 1);
       } else {
         const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
