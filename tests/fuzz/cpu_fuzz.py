@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Differential fuzzing on the CPU: the kernel SOURCE (compiled as host C++ through tests/hostsim) against the
+oracle, on random lines -- statistics, event hash and SCADA records must be identical.
+
+    python tests/fuzz/cpu_fuzz.py [seconds] [first_trial]
+
+Trial t is fully determined by t (line shape, RNG mode, COLD layout, slice boundaries, SCADA capture), so a
+failure is reproduced by `python tests/fuzz/cpu_fuzz.py 1 <t>`.  Companion of tests/fuzz/gpu_fuzz.py (same idea through the
+C ABI on a GPU).  Test tooling: imports oracle/ and tests/."""
+import os, sys, time
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from mjpdes_b200 import abi
+from oracle import binding as O
+from hostsim import binding as H
+from lines import random_line
+from parity import assert_same
+
+
+def one(trial: int):
+    rng = np.random.default_rng(1_700_000 + trial)
+    M = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 20, 31, 32, 33, 40, 64]))
+    K = int(rng.integers(1, 6))
+    kw = dict(jm2dm=bool(rng.random() < .3), up_down=bool(rng.random() < .4),
+              bbs_prob=float(rng.choice([0, .3, .7, 1.0])), reliable_prob=float(rng.choice([0, .1, .5])))
+    run_to = float(rng.choice([60, 150, 400]))
+    line = random_line(rng, M, K, run_to=run_to, warm_up=run_to * float(rng.choice([0, 0.1, 0.5])), **kw)
+    if rng.random() < 0.3:                       # lattice-time line: identical machines -> many ties
+        line.W[:] = 1.0
+        line.w[:] = 1.0
+    if rng.random() < 0.2:
+        line.run_to_job = int(rng.integers(10, 200))
+    mode, n = int(rng.integers(0, 2)), int(rng.integers(1, 4))
+    cold = bool(rng.random() < 0.4)
+    slices = sorted(rng.uniform(0, run_to * 1.2, int(rng.integers(0, 4))).tolist()) if rng.random() < 0.4 else []
+    log = rng.random() < 0.3
+    if log:
+        line.log = True
+        line.max_lines = int(rng.choice([abi.UINT64_MAX, 50, 500]))
+    cap = 300_000 if log else 0
+    want = O.run(line, n, mode=mode, seed=trial, log_capacity=cap)
+    got = H.run(line, n, mode=mode, seed=trial, cold=cold, slices=slices, log_capacity=cap)
+    assert_same(got, want.stats)
+    if log:
+        a, b = np.sort(got.log, order=["instance", "line"]), np.sort(want.log, order=["instance", "line"])
+        assert len(a) == len(b)
+        assert all(np.array_equal(a[f], b[f]) for f in ("clk", "job", "line", "n", "act", "machine"))
+        assert np.array_equal(a["aux"].view(np.uint64), b["aux"].view(np.uint64))
+    return M, K, mode, cold, slices, log
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
+    trial = first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    t0, ok, fails = time.time(), 0, []
+    while time.time() - t0 < budget:
+        try:
+            one(trial)
+            ok += 1
+        except Exception as e:                   # noqa: BLE001 -- every kind of disagreement is a finding
+            fails.append((trial, str(e)[:200]))
+            print("FAIL", fails[-1], flush=True)
+        trial += 1
+    print(f"cpu fuzz: trials {first}..{trial - 1} ok {ok} fails {len(fails)}")
+    print(fails[:10])
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

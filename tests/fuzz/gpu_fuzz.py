@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Differential fuzz on a GPU: random lines through the C ABI vs the CPU oracle (bit-exact compare of status,
-event hash, statistics and SCADA records).   python tools/gpu_fuzz.py [seconds] [first_trial]"""
+event hash, statistics and SCADA records).   python tests/fuzz/gpu_fuzz.py [seconds] [first_trial]"""
 import os, sys, time
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from lines import random_line
