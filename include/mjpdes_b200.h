@@ -134,7 +134,10 @@ typedef struct mjp_line_desc {
 enum { MJP_RNG_COUNTER = 0, MJP_RNG_REPLAY = 1, MJP_RNG_TAPE = 2 };
 
 /* Draw tapes for MJP_RNG_TAPE, instance-major.  `exp` holds the VARIATES sample-exp returned (already
- * divided by the rate).  An instance that runs off a tape ends with MJP_INST_TAPE_EXHAUSTED.           */
+ * divided by the rate).  An instance that runs off a tape ends with MJP_INST_TAPE_EXHAUSTED.  The device
+ * draws lazily: it never needs more of a tape than the reference's own run consumed (end-time realises
+ * up/down events ahead of time, core.clj:138-151), so a tape recorded from a complete reference run is
+ * always sufficient; on a tape cut short it may get further than a look-ahead implementation would.   */
 typedef struct mjp_draw_tapes {
   uint32_t len_jobtype;     /* draws per instance                                                  */
   uint32_t len_uniform;     /* draws per machine per instance                                      */
