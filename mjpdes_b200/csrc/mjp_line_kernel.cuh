@@ -446,6 +446,14 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     for (int k = 0; k < K; ++k) if (choose <= c_thr[k]) return k;
     return -1;
   };
+  // the type of the next job, not consumed (-1: none -- the reference then dies in job-requires, core.clj:240-254)
+  auto next_type = [&]() -> int {
+    if (jt_random) { const int t = (int)(tq & 0xFFu); return t == 0xFF ? -1 : t; }
+    if (!(REPLAY && p.tape_jt != nullptr)) return 0;
+    if (curjob < p.tape_len_jt) return type_from(p.tape_jt[(size_t)g * p.tape_len_jt + curjob]);   // MJP_RNG_TAPE: rand of new-job, core.clj:331
+    flags |= F_TAPE;
+    return -1;
+  };
   // ---- SCADA capture (LOG): :log-buf of the current tick, staged in an L2-resident scratch ----
   // [instance][slot]: the messages of an instance share cache lines with nobody else, so after the first
   // load of a tick the cleaning loops below run out of L1; rows beyond a tick's few messages are never
@@ -729,6 +737,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       live2 = false;
     }
     live = live2;
+    if (live && now_any && c_aj != 0 && next_type() < 0) {
+      // add-job (a "now" candidate, first action of its batch) has no job type to draw: the reference dies in
+      // it before logging anything -- the previous tick is never pushed, nothing of this batch is executed
+      finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED : MJP_INST_JOBTYPE_NIL); live = false;
+    }
     const double tstar = now_any ? clock : tmin;
     MaskT m_f = 0;                                            // future :ends equal to t*
     if (!now_any) {
@@ -761,18 +774,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     // ---- run the batch in generator order, core.clj:742 ----
     if (__any_sync(am, b_aj != 0)) {
       if (b_aj) {                                            // add-job core.clj:240-254
-        int type;
-        if (jt_random) {
-          type = (int)(tq & 0xFFu);
-          if (type == 0xFF) type = -1;
-          tq = ((tq >> 8) & 0xFFFFu) | (((tq >> 24) - 1u) << 24);
-        } else if (!(REPLAY && p.tape_jt != nullptr)) type = 0;
-        else if (curjob < p.tape_len_jt) type = type_from(p.tape_jt[(size_t)g * p.tape_len_jt + curjob]);   // MJP_RNG_TAPE: rand of new-job, core.clj:331
-        else { type = -1; flags |= F_TAPE; }
-        if (type < 0) {                                      // the reference dies in job-requires
-          finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED : MJP_INST_JOBTYPE_NIL); live = false;
-          b_ud = b_tb = b_tm = b_st = b_us = b_bl = b_ub = 0;
-        } else {
+        const int type = next_type();                        // >= 0: checked before the flush above
+        if (jt_random) tq = ((tq >> 8) & 0xFFFFu) | (((tq >> 24) - 1u) << 24);
+        {
           const uint32_t id = curjob + 1;
           start_job(0, type);
           if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }

@@ -2,7 +2,7 @@
 """Differential fuzzing on the CPU: the kernel SOURCE (compiled as host C++ through tests/hostsim) against the
 oracle, on random lines -- statistics, event hash and SCADA records must be identical.
 
-    python tests/fuzz/cpu_fuzz.py [seconds] [first_trial]
+    python tests/fuzz/cpu_fuzz.py [seconds] [first_trial] [wild]
 
 Trial t is fully determined by t (line shape, RNG mode incl. tapes, COLD layout, slice boundaries, SCADA capture), so a
 failure is reproduced by `python tests/fuzz/cpu_fuzz.py 1 <t>`.  Companion of tests/fuzz/gpu_fuzz.py (same idea through the
@@ -18,20 +18,51 @@ from lines import random_line
 from parity import assert_same
 
 
+def wild_line(rng, M, K, run_to, warm_up, n, **kw):
+    """Lines outside the comfortable range of tests/lines.py::random_line: deep buffers, unequal portions (the
+    shifted thresholds of new-job, core.clj:332-339, can then yield no job type at all), failure-prone or slow-to-
+    repair machines, wide spreads of processing times, per-instance override planes."""
+    lam = np.where(rng.random(M) < 0.1, 0.0, rng.choice([0.005, 0.05, 0.3, 1.0, 3.0], M) * rng.uniform(0.5, 1.5, M))
+    mu = rng.choice([0.05, 0.3, 1.0, 5.0, 50.0], M) * rng.uniform(0.5, 1.5, M)
+    W = rng.choice([0.2, 1.0, 1.0, 3.0], M) * rng.uniform(0.8, 1.2, M)
+    N = rng.choice([1, 1, 2, 3, 8, 40, 254], M - 1)
+    portion = rng.dirichlet(np.ones(K)) if rng.random() < 0.5 else np.full(K, 1.0 / K)
+    portion = np.maximum(portion, 1e-3)
+    w = rng.choice([0.05, 0.5, 1.0, 1.0, 2.0, 7.5], size=(K, M))
+    planes = {}
+    if rng.random() < 0.3:
+        planes = dict(W_inst=rng.uniform(0.5, 2.0, (M, n)), N_inst=rng.integers(1, N[:, None] + 1, (M - 1, n)).astype(np.int32))
+        if rng.random() < 0.5:
+            planes.update(lam_inst=rng.uniform(0.0, 0.5, (M, n)), mu_inst=rng.uniform(0.2, 3.0, (M, n)),
+                          w_inst=rng.uniform(0.3, 3.0, (K * M, n)))
+    return abi.HostLine(lam=lam, mu=mu, W=W, discipline=rng.random(M) < rng.choice([0, .3, 1.0]), N=N, portion=portion, w=w,
+                        warm_up=warm_up, run_to=run_to, **planes, **kw)
+
+
+WILD = False
+
+
 def one(trial: int):
     rng = np.random.default_rng(1_700_000 + trial)
     M = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 20, 31, 32, 33, 40, 64]))
-    K = int(rng.integers(1, 6))
+    K = int(rng.integers(1, 6)) if not WILD else int(rng.choice([1, 2, 3, 7, 16, 40]))
     kw = dict(jm2dm=bool(rng.random() < .3), up_down=bool(rng.random() < .4),
               bbs_prob=float(rng.choice([0, .3, .7, 1.0])), reliable_prob=float(rng.choice([0, .1, .5])))
     run_to = float(rng.choice([60, 150, 400]))
-    line = random_line(rng, M, K, run_to=run_to, warm_up=run_to * float(rng.choice([0, 0.1, 0.5])), **kw)
+    if WILD:
+        n_w = int(rng.integers(1, 4))
+        line = wild_line(rng, M, K, run_to, run_to * float(rng.choice([0, 0.1, 0.5])), n_w,
+                         jm2dm=kw["jm2dm"], up_down=kw["up_down"])
+    else:
+        line = random_line(rng, M, K, run_to=run_to, warm_up=run_to * float(rng.choice([0, 0.1, 0.5])), **kw)
     if rng.random() < 0.3:                       # lattice-time line: identical machines -> many ties
         line.W[:] = 1.0
         line.w[:] = 1.0
     if rng.random() < 0.2:
         line.run_to_job = int(rng.integers(10, 200))
     mode, n = int(rng.integers(0, 2)), int(rng.integers(1, 4))
+    if WILD:
+        n = n_w
     cold = bool(rng.random() < 0.4)
     slices = sorted(rng.uniform(0, run_to * 1.2, int(rng.integers(0, 4))).tolist()) if rng.random() < 0.4 else []
     log = rng.random() < 0.3
@@ -67,8 +98,10 @@ def one(trial: int):
 
 
 def main():
+    global WILD
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
     trial = first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    WILD = len(sys.argv) > 3 and sys.argv[3] == "wild"
     t0, ok, fails = time.time(), 0, []
     while time.time() - t0 < budget:
         try:

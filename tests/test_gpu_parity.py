@@ -100,6 +100,13 @@ def test_status_codes(engine, oracle):
     got, want = engine.run(line, 33, seed=1).stats, oracle.run(line, 33, seed=1).stats
     assert set(want.status.tolist()) == {abi.INST_JOBTYPE_NIL}
     assert np.array_equal(got.status, want.status)
+    # an instance that dies later leaves the same event count and accumulators behind (the tick before the fatal
+    # add-job is never pushed)
+    line = abi.HostLine(lam=[.1, .1, .1], mu=[.9, .9, .9], W=[1., 1., 1.], discipline=[0, 1, 0], N=[2, 1],
+                        portion=[0.45, 0.55], w=np.ones((2, 3)), warm_up=0, run_to=500)
+    got, want = engine.run(line, 70, seed=1).stats, oracle.run(line, 70, seed=1).stats
+    assert set(want.status.tolist()) == {abi.INST_JOBTYPE_NIL} and want.n_events.max() > 50
+    assert_same(got, want)
 
 
 def test_invalid_descriptors_are_rejected(engine):
