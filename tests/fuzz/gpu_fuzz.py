@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzz on a GPU: random lines through the C ABI vs the CPU oracle (bit-exact compare of status,
-event hash, statistics and SCADA records).   python tests/fuzz/gpu_fuzz.py [seconds] [first_trial]"""
+event hash, statistics and SCADA records).   python tests/fuzz/gpu_fuzz.py [seconds] [first_trial] [wild]
+`wild` draws the lines from cpu_fuzz.wild_line (deep buffers, unequal portions, extreme rates, override planes)."""
 import os, sys, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,9 +10,12 @@ from lines import random_line
 from mjpdes_b200 import abi, engine
 from oracle import binding as O
 from parity import assert_same
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from cpu_fuzz import wild_line
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
 trial = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+wild = len(sys.argv) > 3 and sys.argv[3] == "wild"
 t0, ok, fails = time.time(), 0, []
 with engine.Handle(device=0, event_hash=True) as h:
     while time.time() - t0 < budget:
@@ -21,13 +25,18 @@ with engine.Handle(device=0, event_hash=True) as h:
         kw = dict(jm2dm=bool(rng.random() < .3), up_down=bool(rng.random() < .4), bbs_prob=float(rng.choice([0, .3, .7, 1.0])),
                   reliable_prob=float(rng.choice([0, .1, .5])))
         run_to = float(rng.choice([60, 150, 400]))
-        line = random_line(rng, M, K, run_to=run_to, warm_up=run_to * float(rng.choice([0, 0.1, 0.5])), **kw)
+        n = int(rng.choice([1, 31, 33, 64, 97, 200]))
+        if wild:
+            K = int(rng.choice([1, 2, 3, 7, 16, 40]))
+            line = wild_line(rng, M, K, run_to, run_to * float(rng.choice([0, 0.1, 0.5])), n, jm2dm=kw["jm2dm"],
+                             up_down=kw["up_down"])
+        else:
+            line = random_line(rng, M, K, run_to=run_to, warm_up=run_to * float(rng.choice([0, 0.1, 0.5])), **kw)
         if rng.random() < 0.3:
             line.W[:] = 1.0; line.w[:] = 1.0
         if rng.random() < 0.2:
             line.run_to_job = int(rng.integers(10, 200))
         mode = int(rng.integers(0, 2))
-        n = int(rng.choice([1, 31, 33, 64, 97, 200]))
         log = rng.random() < 0.3
         slices = sorted(rng.uniform(0, run_to * 1.2, int(rng.integers(1, 4))).tolist()) if rng.random() < 0.3 else []
         cap = 0
