@@ -169,3 +169,16 @@ def test_time_slicing_with_scada_log(oracle):
         assert np.array_equal(a[f], b[f]), f
     assert np.array_equal(a["aux"].view(np.uint64), b["aux"].view(np.uint64))
     assert_same(got, want.stats)
+
+
+def test_fuzz_profiles_sample(oracle):
+    """A fixed sample of both profiles of tests/fuzz/cpu_fuzz.py (standard: trials 0.., incl. MJP_RNG_TAPE, COLD, slices
+    and SCADA capture; wild: deep buffers, unequal portions, extreme rates, override planes)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
+    import cpu_fuzz
+    for wild, first in ((False, 0), (True, 3_000_000)):
+        cpu_fuzz.WILD = wild
+        for t in range(first, first + 300):
+            cpu_fuzz.one(t)
+    cpu_fuzz.WILD = False
