@@ -774,45 +774,43 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     // ---- run the batch in generator order, core.clj:742 ----
     if (__any_sync(am, b_aj != 0)) {
       if (b_aj) {                                            // add-job core.clj:240-254
-        const int type = next_type();                        // >= 0: checked before the flush above
+        const int type = next_type();                        // >= 0: checked when the batch was formed
         if (jt_random) tq = ((tq >> 8) & 0xFFFFu) | (((tq >> 24) - 1u) << 24);
-        {
-          const uint32_t id = curjob + 1;
-          start_job(0, type);
-          if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
-          mark_seen(0);
-          if (LOG) {
-            stage_msg(MJP_ACT_AJ, 0, type, id);
-            // the :aj record carries :ends (core.clj:250): when the lazy end-time is still pending, run the
-            // literal look-ahead of core.clj:141-151 over events that are generated but not committed
-            if (!(pend & 1)) aj_ends = get_end(0);
-            else {
-              double rem = get_end(0), t = FUT_T(0), v;
-              uint32_t n = FUT_N(0), ecur = REPLAY ? s_eidx[0] : 0u;
-              bool have_nxt = !(need & 1);                     // event n+1 is already realised in NXT_T(0)
-              auto after = [&](bool prev_is_up, double t_prev) -> double {
-                double r;
-                if (have_nxt) { r = NXT_T(0); have_nxt = false; }
-                else r = next_event_time(0, n, prev_is_up, t_prev, ecur);
-                ++n;
-                return r;
-              };
-              if (up & 1) t = after(false, t);                 // the :up after the pending :down
-              for (;;) {
-                const double t_dn = after(true, t);
-                if (!(t_dn == t_dn)) { v = QNAN; flags |= F_TAPE; break; }       // tape exhausted
-                if (!end_time_resume(t, t_dn, rem, v)) break;
-                rem = v;
-                t = after(false, t_dn);
-              }
-              aj_ends = v;
+        const uint32_t id = curjob + 1;
+        start_job(0, type);
+        if (HASH) { hmix(h, (uint64_t)MJP_ACT_AJ | ((uint64_t)type << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
+        mark_seen(0);
+        if (LOG) {
+          stage_msg(MJP_ACT_AJ, 0, type, id);
+          // the :aj record carries :ends (core.clj:250): when the lazy end-time is still pending, run the
+          // literal look-ahead of core.clj:141-151 over events that are generated but not committed
+          if (!(pend & 1)) aj_ends = get_end(0);
+          else {
+            double rem = get_end(0), t = FUT_T(0), v;
+            uint32_t n = FUT_N(0), ecur = REPLAY ? s_eidx[0] : 0u;
+            bool have_nxt = !(need & 1);                     // event n+1 is already realised in NXT_T(0)
+            auto after = [&](bool prev_is_up, double t_prev) -> double {
+              double r;
+              if (have_nxt) { r = NXT_T(0); have_nxt = false; }
+              else r = next_event_time(0, n, prev_is_up, t_prev, ecur);
+              ++n;
+              return r;
+            };
+            if (up & 1) t = after(false, t);                 // the :up after the pending :down
+            for (;;) {
+              const double t_dn = after(true, t);
+              if (!(t_dn == t_dn)) { v = QNAN; flags |= F_TAPE; break; }       // tape exhausted
+              if (!end_time_resume(t, t_dn, rem, v)) break;
+              rem = v;
+              t = after(false, t_dn);
             }
+            aj_ends = v;
           }
-          curjob = id; occ |= 1; STARTED(0) = id;
-          if (K > 1) setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
-          p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
-          if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
         }
+        curjob = id; occ |= 1; STARTED(0) = id;
+        if (K > 1) setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
+        p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
+        if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
       }
     }
     {
