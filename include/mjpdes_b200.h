@@ -246,6 +246,36 @@ int mjp_last_kernel_ms(mjp_handle *h, float *ms);
 /* number of kernels launched by the last mjp_launch() */
 int mjp_last_launch_count(mjp_handle *h, int *n);
 
+/* Device address of the aggregate vector of the last launch (mjp_aggregate_len doubles, valid after mjp_sync and
+ * until the next mjp_upload): lets a multi-process host reduce it across ranks with NCCL without a host round trip. */
+int mjp_device_aggregate(mjp_handle *h, double **device_ptr, int32_t *len);
+
+/* ---- all GPUs of one box behind one call --------------------------------------- */
+/* main-loop-multi (core.clj:746-766) fans the replications out over JVM futures; mjp_multi_run() fans a batch out
+ * over the devices of one box: contiguous ranges of instance ids, ceil(n/G) per device (an instance's random
+ * substreams depend on its id only, so results do not depend on G), one host thread and one stream per device, no
+ * exchange while simulating.  The only collective is the sum of the per-device aggregate vectors:
+ *   MJP_REDUCE_PEER  device 0 gathers them with peer copies over NVLink and adds them in device order;
+ *   MJP_REDUCE_NCCL  ncclAllReduce(sum, f64); libnccl.so.2 is bound at run time (MJP_ERR_UNSUPPORTED if absent).
+ * `stats` planes are [rows][n_inst] over the WHOLE batch (each device fills its columns); stats->aggregate
+ * receives the reduced vector.  SCADA capture stays per device (use one mjp_handle per device for it).         */
+enum { MJP_REDUCE_PEER = 0, MJP_REDUCE_NCCL = 1 };
+typedef struct mjp_multi_config {
+  int32_t n_devices;        /* 0 = every visible device                         */
+  const int32_t *devices;   /* [n_devices] CUDA ordinals; NULL = 0..n_devices-1 */
+  int32_t flags;            /* MJP_CFG_* for every per-device handle            */
+  int32_t reduce;           /* MJP_REDUCE_*                                     */
+} mjp_multi_config;
+typedef struct mjp_multi mjp_multi;
+int  mjp_multi_create(const mjp_multi_config *cfg, mjp_multi **out);
+void mjp_multi_destroy(mjp_multi *m);
+const char *mjp_multi_last_error(const mjp_multi *m);   /* m may be NULL: last create error */
+int  mjp_multi_device_count(const mjp_multi *m);
+int  mjp_multi_run(mjp_multi *m, const mjp_line_desc *line, uint64_t n_inst, const mjp_rng_spec *rng,
+                   mjp_stats_out *stats);
+/* device time of the last mjp_multi_run: max over devices of the kernel time, and the reduction */
+int  mjp_multi_last_ms(mjp_multi *m, float *kernel_ms_max, float *reduce_ms);
+
 /* Probe of one device function: end-time (core.clj:138-151) over a literal
  * :up&down schedule, the seam the reference's own tests use (core_test.clj:26-93).
  * kinds[j]: 0 = :up, 1 = :down.                                               */

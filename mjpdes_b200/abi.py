@@ -113,6 +113,14 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_int32), ("max_instances", C.c_uint64)]
 
 
+REDUCE_PEER, REDUCE_NCCL = 0, 1
+
+
+class MultiConfig(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)), ("flags", C.c_int32),
+                ("reduce", C.c_int32)]
+
+
 def aggregate_len(M: int) -> int:
     return 1 + 2 * (3 * M + 1)
 
@@ -272,6 +280,15 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.mjp_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.mjp_last_launch_count.argtypes = [H, C.POINTER(C.c_int)]
     lib.mjp_probe_end_time.argtypes = [H, _pu8, _pd, C.c_int32, C.c_double, C.c_double, _pd]
+    lib.mjp_device_aggregate.argtypes = [H, C.POINTER(_pd), C.POINTER(C.c_int32)]
+    lib.mjp_multi_create.argtypes = [C.POINTER(MultiConfig), C.POINTER(H)]
+    lib.mjp_multi_destroy.argtypes = [H]
+    lib.mjp_multi_destroy.restype = None
+    lib.mjp_multi_last_error.argtypes = [H]
+    lib.mjp_multi_last_error.restype = C.c_char_p
+    lib.mjp_multi_device_count.argtypes = [H]
+    lib.mjp_multi_run.argtypes = [H, C.POINTER(LineDesc), C.c_uint64, C.POINTER(RngSpec), C.POINTER(StatsOut)]
+    lib.mjp_multi_last_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     if lib.mjp_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI version mismatch: library {lib.mjp_abi_version()} vs binding {ABI_VERSION}")
     if path is None:
@@ -282,5 +299,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "mjp_abi_version", "mjp_device_count", "mjp_aggregate_len", "mjp_create", "mjp_destroy", "mjp_last_error",
     "mjp_run", "mjp_upload", "mjp_set_tapes", "mjp_reserve_log", "mjp_launch", "mjp_launch_slice", "mjp_sync", "mjp_download", "mjp_last_kernel_ms",
-    "mjp_last_launch_count", "mjp_probe_end_time",
+    "mjp_last_launch_count", "mjp_probe_end_time", "mjp_device_aggregate",
+    "mjp_multi_create", "mjp_multi_destroy", "mjp_multi_last_error", "mjp_multi_device_count", "mjp_multi_run",
+    "mjp_multi_last_ms",
 ]

@@ -8,13 +8,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <limits>
 #include <string>
 #include <vector>
 
 #include "../../include/mjpdes_b200.h"
-#include "mjp_line_kernel.cuh"
+#include "mjp_aux_kernels.cuh"
+#include "mjp_launch.cuh"
 #include "mjp_plan.h"
 
 namespace {
@@ -60,6 +62,8 @@ struct mjp_handle {
   int last_launches = 0;
   int block_threads = 0;
   size_t smem_bytes = 0;
+  // what the launch that parked the current state looked like (a resume must match it)
+  struct ParkKey { int mode = -1, log = 0, cold = 0, threads = 0; uint64_t seed = 0, first_id = 0; } park_key;
 };
 
 #define CK(call)                                                                                   \
@@ -79,7 +83,7 @@ static int fail(mjp_handle *h, int code, const char *msg) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 /* the checks of core.clj:75-121 (clojure.spec) that concern the loop, plus the kernel's own limits */
-static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
+static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst, uint64_t lo, uint64_t n_total) {
   if (!L) return fail(h, MJP_ERR_INVALID, "line descriptor is NULL");
   if (n_inst == 0) return fail(h, MJP_ERR_INVALID, "n_inst must be >= 1");
   if (n_inst >= (1ull << 31)) return fail(h, MJP_ERR_UNSUPPORTED, "2^31 or more instances per call");
@@ -90,9 +94,9 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   if (!L->lambda || !L->mu || !L->W || !L->discipline || !L->N || !L->portion || !L->w)
     return fail(h, MJP_ERR_INVALID, "a required array of the line descriptor is NULL");
   for (int i = 0; i < L->M; ++i) {
-    if (!(L->lambda[i] >= 0.0)) return fail(h, MJP_ERR_INVALID, ":lambda must be non-negative (core.clj:89)");
-    if (!(L->mu[i] > 0.0)) return fail(h, MJP_ERR_INVALID, ":mu must be positive (core.clj:88)");
-    if (!(L->W[i] > 0.0)) return fail(h, MJP_ERR_INVALID, ":W must be positive (core.clj:87)");
+    if (!(L->lambda[i] >= 0.0) || !std::isfinite(L->lambda[i])) return fail(h, MJP_ERR_INVALID, ":lambda must be non-negative and finite (core.clj:89)");
+    if (!(L->mu[i] > 0.0) || !std::isfinite(L->mu[i])) return fail(h, MJP_ERR_INVALID, ":mu must be positive and finite (core.clj:88)");
+    if (!(L->W[i] > 0.0) || !std::isfinite(L->W[i])) return fail(h, MJP_ERR_INVALID, ":W must be positive and finite (core.clj:87)");
     if (L->discipline[i] > 1) return fail(h, MJP_ERR_INVALID, ":discipline must be :BAS or :BBS (core.clj:91)");
   }
   for (int b = 0; b < L->M - 1; ++b) {
@@ -100,52 +104,36 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
     if (L->N[b] > 254) return fail(h, MJP_ERR_UNSUPPORTED, "buffer capacity above 254");
   }
   for (int k = 0; k < L->K; ++k)
-    if (!(L->portion[k] > 0.0)) return fail(h, MJP_ERR_INVALID, ":portion must be positive (core.clj:109)");
+    if (!(L->portion[k] > 0.0) || !std::isfinite(L->portion[k])) return fail(h, MJP_ERR_INVALID, ":portion must be positive and finite (core.clj:109)");
   for (int q = 0; q < L->K * L->M; ++q)
-    if (!(L->w[q] > 0.0)) return fail(h, MJP_ERR_INVALID, ":w values must be positive (core.clj:108)");
-  if (!(L->warm_up >= 0.0)) return fail(h, MJP_ERR_INVALID, ":warm-up-time must be non-negative (core.clj:104)");
+    if (!(L->w[q] > 0.0) || !std::isfinite(L->w[q])) return fail(h, MJP_ERR_INVALID, ":w values must be positive and finite (core.clj:108)");
+  if (!(L->warm_up >= 0.0) || !std::isfinite(L->warm_up)) return fail(h, MJP_ERR_INVALID, ":warm-up-time must be non-negative and finite (core.clj:104)");
+  // +inf is allowed here (main-loop-continuous never ends, core.clj:801-843); mjp_launch_slice refuses to run it unsliced
   if (!(L->run_to > 0.0)) return fail(h, MJP_ERR_INVALID, ":run-to-time must be positive (core.clj:105)");
+  // per-instance planes are [rows][n_total]; this call covers columns lo .. lo + n_inst
+  auto plane_ok = [&](const double *pl, int rows, bool allow_zero) {
+    for (int r = 0; r < rows; ++r)
+      for (uint64_t g = 0; g < n_inst; ++g) {
+        const double v = pl[(size_t)r * n_total + lo + g];
+        if (!(allow_zero ? v >= 0.0 : v > 0.0) || !std::isfinite(v)) return false;
+      }
+    return true;
+  };
   if (L->N_inst)
     for (int b = 0; b < L->M - 1; ++b)
       for (uint64_t g = 0; g < n_inst; ++g) {
-        const int v = L->N_inst[(size_t)b * n_inst + g];
+        const int v = L->N_inst[(size_t)b * n_total + lo + g];
         if (v < 1 || v > L->N[b]) return fail(h, MJP_ERR_INVALID, "N_inst value outside 1..N[b]");
       }
-  const uint64_t nm = n_inst * (uint64_t)L->M, nkm = n_inst * (uint64_t)L->M * (uint64_t)L->K;
-  if (L->lambda_inst) for (uint64_t q = 0; q < nm; ++q) if (!(L->lambda_inst[q] >= 0.0)) return fail(h, MJP_ERR_INVALID, "lambda_inst must be non-negative");
-  if (L->mu_inst) for (uint64_t q = 0; q < nm; ++q) if (!(L->mu_inst[q] > 0.0)) return fail(h, MJP_ERR_INVALID, "mu_inst must be positive");
-  if (L->W_inst) for (uint64_t q = 0; q < nm; ++q) if (!(L->W_inst[q] > 0.0)) return fail(h, MJP_ERR_INVALID, "W_inst must be positive");
-  if (L->w_inst) for (uint64_t q = 0; q < nkm; ++q) if (!(L->w_inst[q] > 0.0)) return fail(h, MJP_ERR_INVALID, "w_inst must be positive");
+  if (L->lambda_inst && !plane_ok(L->lambda_inst, L->M, true)) return fail(h, MJP_ERR_INVALID, "lambda_inst must be non-negative and finite");
+  if (L->mu_inst && !plane_ok(L->mu_inst, L->M, false)) return fail(h, MJP_ERR_INVALID, "mu_inst must be positive and finite");
+  if (L->W_inst && !plane_ok(L->W_inst, L->M, false)) return fail(h, MJP_ERR_INVALID, "W_inst must be positive and finite");
+  if (L->w_inst && !plane_ok(L->w_inst, L->K * L->M, false)) return fail(h, MJP_ERR_INVALID, "w_inst must be positive and finite");
   return MJP_OK;
 }
 
-template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SLICE, bool LOG, bool COLD>
-static cudaError_t launch_variant(const mjp::KParams &kp, int blocks, int threads, size_t smem, cudaStream_t st) {
-  auto k = mjp::mjp_line_kernel<MaskT, MT, REPLAY, HASH, SLICE, LOG, COLD>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<blocks, threads, smem, st>>>(kp);
-  return cudaGetLastError();
-}
-
-template <typename MaskT, int MT, bool COLD = false>
-static cudaError_t launch_flags(bool replay, bool hash, bool slice, bool log, const mjp::KParams &kp, int blocks,
-                                int threads, size_t smem, cudaStream_t st) {
-  const int v = (replay ? 4 : 0) | (hash ? 2 : 0) | (slice ? 1 : 0);
-#define MJP_CASE(n, LG) \
-  case n: return launch_variant<MaskT, MT, ((n) & 4) != 0, ((n) & 2) != 0, ((n) & 1) != 0, LG, COLD>(kp, blocks, threads, smem, st);
-  if (log) {
-    switch (v) {
-      MJP_CASE(0, true) MJP_CASE(1, true) MJP_CASE(2, true) MJP_CASE(3, true)
-      MJP_CASE(4, true) MJP_CASE(5, true) MJP_CASE(6, true) default: MJP_CASE(7, true)
-    }
-  }
-  switch (v) {
-    MJP_CASE(0, false) MJP_CASE(1, false) MJP_CASE(2, false) MJP_CASE(3, false)
-    MJP_CASE(4, false) MJP_CASE(5, false) MJP_CASE(6, false) default: MJP_CASE(7, false)
-  }
-#undef MJP_CASE
-}
+static int upload_impl(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst, uint64_t lo, uint64_t n_total);
+static int download_impl(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log, uint64_t lo, uint64_t n_total);
 
 static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
   static const bool force_generic = std::getenv("MJP_FORCE_GENERIC") != nullptr;   // A/B measurements only
@@ -155,23 +143,25 @@ static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
 
 static cudaError_t launch_line_kernel(bool replay, bool hash, bool slice, bool log, bool cold, const mjp::KParams &kp,
                                       int blocks, int threads, size_t smem, cudaStream_t st) {
-#define MJP_ARGS replay, hash, slice, log, kp, blocks, threads, smem, st
-  if (cold) return kp.M > 32 ? launch_flags<uint64_t, 0, true>(MJP_ARGS) : launch_flags<uint32_t, 0, true>(MJP_ARGS);
-  if (kp.M > 32) return launch_flags<uint64_t, 0>(MJP_ARGS);
+#define MJP_GO(T, MT, COLD)                                                                          \
+  return log ? mjp::launch_flags<T, MT, COLD, true>(replay, hash, slice, kp, blocks, threads, smem, st) \
+             : mjp::launch_flags<T, MT, COLD, false>(replay, hash, slice, kp, blocks, threads, smem, st)
+  if (cold) { if (kp.M > 32) MJP_GO(uint64_t, 0, true); MJP_GO(uint32_t, 0, true); }
+  if (kp.M > 32) MJP_GO(uint64_t, 0, false);
   if (use_register_ends(kp, log, threads)) {
     switch (kp.M) {
-      case 2: return launch_flags<uint32_t, 2>(MJP_ARGS);
-      case 3: return launch_flags<uint32_t, 3>(MJP_ARGS);
-      case 4: return launch_flags<uint32_t, 4>(MJP_ARGS);
-      case 5: return launch_flags<uint32_t, 5>(MJP_ARGS);
-      case 6: return launch_flags<uint32_t, 6>(MJP_ARGS);
-      case 7: return launch_flags<uint32_t, 7>(MJP_ARGS);
-      case 8: return launch_flags<uint32_t, 8>(MJP_ARGS);
+      case 2: MJP_GO(uint32_t, 2, false);
+      case 3: MJP_GO(uint32_t, 3, false);
+      case 4: MJP_GO(uint32_t, 4, false);
+      case 5: MJP_GO(uint32_t, 5, false);
+      case 6: MJP_GO(uint32_t, 6, false);
+      case 7: MJP_GO(uint32_t, 7, false);
+      case 8: MJP_GO(uint32_t, 8, false);
       default: break;
     }
   }
-  return launch_flags<uint32_t, 0>(MJP_ARGS);
-#undef MJP_ARGS
+  MJP_GO(uint32_t, 0, false);
+#undef MJP_GO
 }
 
 extern "C" {
@@ -225,10 +215,16 @@ void mjp_destroy(mjp_handle *h) {
 
 const char *mjp_last_error(const mjp_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
+int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) { return upload_impl(h, L, n_inst, 0, n_inst); }
+
+}  // extern "C"
+
+// Upload instances [lo, lo + n_inst) of a batch of n_total: the per-instance override planes of the descriptor are
+// [rows][n_total] and only this window of columns is copied (2-D copies); mjp_upload is the window [0, n).
+static int upload_impl(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst, uint64_t lo, uint64_t n_total) {
   if (!h) return MJP_ERR_INVALID;
   h->uploaded = false; h->launched = false;
-  int rc = validate(h, L, n_inst);
+  int rc = validate(h, L, n_inst, lo, n_total);
   if (rc != MJP_OK) return rc;
   CK(cudaSetDevice(h->device));
   const int M = L->M, K = L->K;
@@ -259,18 +255,19 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
     CK(h->d_planes.reserve(need));
     char *base = (char *)h->d_planes.ptr;
     size_t off = 0;
-    auto put = [&](const void *src, size_t bytes, size_t padded) -> const void * {
+    auto put = [&](const void *src, size_t elem, size_t rows, size_t padded) -> const void * {
       if (!src) return nullptr;
       void *dst = base + off;
-      cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+      cudaMemcpy2DAsync(dst, n_inst * elem, (const char *)src + lo * elem, n_total * elem, n_inst * elem, rows,
+                        cudaMemcpyHostToDevice, h->stream);
       off += padded;
       return dst;
     };
-    kp.lam_i = (const double *)put(L->lambda_inst, n_inst * M * sizeof(double), pM);
-    kp.mu_i = (const double *)put(L->mu_inst, n_inst * M * sizeof(double), pM);
-    kp.W_i = (const double *)put(L->W_inst, n_inst * M * sizeof(double), pM);
-    kp.w_i = (const double *)put(L->w_inst, n_inst * (size_t)K * M * sizeof(double), pKM);
-    kp.N_i = (const int32_t *)put(L->N_inst, n_inst * (size_t)(M - 1) * sizeof(int32_t), pN);
+    kp.lam_i = (const double *)put(L->lambda_inst, sizeof(double), M, pM);
+    kp.mu_i = (const double *)put(L->mu_inst, sizeof(double), M, pM);
+    kp.W_i = (const double *)put(L->W_inst, sizeof(double), M, pM);
+    kp.w_i = (const double *)put(L->w_inst, sizeof(double), (size_t)K * M, pKM);
+    kp.N_i = (const int32_t *)put(L->N_inst, sizeof(int32_t), (size_t)(M - 1), pN);
     CK(cudaGetLastError());
   }
 
@@ -306,6 +303,8 @@ int mjp_upload(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst) {
   h->uploaded = true;
   return MJP_OK;
 }
+
+extern "C" {
 
 int mjp_reserve_log(mjp_handle *h, uint64_t capacity) {
   if (!h) return MJP_ERR_INVALID;
@@ -352,6 +351,10 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     return fail(h, MJP_ERR_INVALID, "bad mjp_rng_spec");
   if (rng->mode == MJP_RNG_TAPE && !h->kp.tape_u)
     return fail(h, MJP_ERR_INVALID, "MJP_RNG_TAPE: call mjp_set_tapes after mjp_upload first");
+  // the kernel's only exits are the horizon, :run-to-job and the slice boundary: without any of them it would
+  // spin for ever on a healthy line (main-loop-continuous, core.clj:801-843, must be driven in slices)
+  if (until == std::numeric_limits<double>::infinity() && !std::isfinite(h->kp.run_to) && h->kp.run_to_job < 0)
+    return fail(h, MJP_ERR_INVALID, "endless run: :run-to-time is infinite, no :run-to-job, no slice boundary");
   CK(cudaSetDevice(h->device));
   mjp::KParams &kp = h->kp;
   kp.seed = rng->seed;
@@ -395,6 +398,18 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     else if (fits(true, 32)) { threads = 32; cold = true; }
     else return fail(h, MJP_ERR_UNSUPPORTED, "line state does not fit in shared memory (M, sum N too large)");
     h->block_threads = threads;
+    {
+      // the park layout follows from the variant: a resume must be the same kind of launch on the same substreams
+      mjp_handle::ParkKey key;
+      key.mode = rng->mode; key.log = h->want_log; key.cold = cold; key.threads = threads;
+      key.seed = rng->seed; key.first_id = rng->first_instance_id;
+      const mjp_handle::ParkKey &k0 = h->park_key;
+      if (resume && (k0.mode != key.mode || k0.log != key.log || k0.cold != key.cold || k0.threads != key.threads ||
+                     k0.seed != key.seed || k0.first_id != key.first_id))
+        return fail(h, MJP_ERR_INVALID, "resume does not match the launch that parked the state (rng mode, seed, "
+                                        "first_instance_id and want_log must be the same)");
+      h->park_key = key;
+    }
     const bool mt = !cold && use_register_ends(kp, h->want_log, threads);
     const size_t per_thread = mjp::plan_layout(kp, mt, replay, h->want_log, cold);
     if (cold) {
@@ -447,25 +462,44 @@ int mjp_sync(mjp_handle *h) {
 }
 
 int mjp_download(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log) {
+  return download_impl(h, s, log, 0, h ? h->kp.n_inst : 0);
+}
+
+int mjp_device_aggregate(mjp_handle *h, double **dptr, int32_t *len) {
+  if (!h || !dptr) return MJP_ERR_INVALID;
+  if (!h->launched) return fail(h, MJP_ERR_INVALID, "mjp_device_aggregate before mjp_launch");
+  *dptr = h->d_agg.as<double>();
+  if (len) *len = mjp_aggregate_len(h->kp.M);
+  return MJP_OK;
+}
+
+}  // extern "C"
+
+// Copy the results of this handle's instances into columns lo .. lo + n of caller planes that are n_total wide
+// (mjp_download: lo = 0, n_total = n).
+static int download_impl(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log, uint64_t lo, uint64_t n_total) {
   if (!h) return MJP_ERR_INVALID;
   if (!h->launched) return fail(h, MJP_ERR_INVALID, "mjp_download before mjp_launch");
   CK(cudaSetDevice(h->device));
   const mjp::KParams &kp = h->kp;
   const size_t n = kp.n_inst;
   const char *ob = (const char *)h->d_out.ptr;
-  auto get = [&](void *dst, size_t o, size_t bytes) {
-    if (dst) cudaMemcpyAsync(dst, ob + o, bytes, cudaMemcpyDeviceToHost, h->stream);
+  auto get = [&](void *dst, size_t o, size_t elem, size_t rows) {
+    if (!dst) return;
+    if (n_total == n) cudaMemcpyAsync(dst, ob + o, n * elem * rows, cudaMemcpyDeviceToHost, h->stream);
+    else cudaMemcpy2DAsync((char *)dst + lo * elem, n_total * elem, ob + o, n * elem, n * elem, rows,
+                           cudaMemcpyDeviceToHost, h->stream);
   };
   if (s) {
-    get(s->njobs, h->o_njobs, n * 8); get(s->residence_sum, h->o_res, n * 8);
-    get(s->blocked_time, h->o_blk, n * kp.M * 8); get(s->starved_time, h->o_stv, n * kp.M * 8);
-    get(s->occ_time, h->o_occ, n * (size_t)kp.L * 8); get(s->final_clock, h->o_clk, n * 8);
-    get(s->current_job, h->o_cur, n * 8); get(s->n_events, h->o_nev, n * 8);
+    get(s->njobs, h->o_njobs, 8, 1); get(s->residence_sum, h->o_res, 8, 1);
+    get(s->blocked_time, h->o_blk, 8, kp.M); get(s->starved_time, h->o_stv, 8, kp.M);
+    get(s->occ_time, h->o_occ, 8, (size_t)kp.L); get(s->final_clock, h->o_clk, 8, 1);
+    get(s->current_job, h->o_cur, 8, 1); get(s->n_events, h->o_nev, 8, 1);
     if (s->event_hash) {
-      if (h->flags & MJP_CFG_EVENT_HASH) get(s->event_hash, h->o_hash, n * 8);
-      else std::memset(s->event_hash, 0, n * 8);
+      if (h->flags & MJP_CFG_EVENT_HASH) get(s->event_hash, h->o_hash, 8, 1);
+      else std::memset(s->event_hash + lo, 0, n * 8);
     }
-    get(s->status, h->o_status, n);
+    get(s->status, h->o_status, 1, 1);
     if (s->aggregate)
       cudaMemcpyAsync(s->aggregate, h->d_agg.ptr, (size_t)mjp_aggregate_len(kp.M) * 8, cudaMemcpyDeviceToHost, h->stream);
   }
@@ -490,6 +524,8 @@ int mjp_download(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log) {
   CK(cudaStreamSynchronize(h->stream));
   return rc;
 }
+
+extern "C" {
 
 int mjp_run(mjp_handle *h, const mjp_line_desc *line, uint64_t n_inst, const mjp_rng_spec *rng,
             mjp_stats_out *stats, mjp_log_out *log) {
@@ -536,6 +572,241 @@ int mjp_probe_end_time(mjp_handle *h, const uint8_t *kinds, const double *times,
   e = cudaStreamSynchronize(h->stream);
   buf.release();
   if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return MJP_ERR_CUDA; }
+  return MJP_OK;
+}
+
+}  // extern "C"
+
+// ================= multi-GPU: main-loop-multi's fan-out (core.clj:753-766) over the GPUs of one box =================
+// One mjp_handle and one host thread per device; the batch is cut into contiguous ranges of instance ids (an
+// instance's random substreams depend on its id only, so the results do not depend on the number of devices).
+// There is no data-path exchange.  The ONE collective is the sum of the per-device aggregate vectors:
+//   MJP_REDUCE_PEER  device 0 pulls every vector over NVLink (cudaMemcpyPeerAsync) and sums them in device order
+//                    (deterministic: the result does not depend on timing);
+//   MJP_REDUCE_NCCL  ncclAllReduce(sum, f64) over communicators made by ncclCommInitAll; libnccl.so.2 is bound at
+//                    run time (dlopen), so the library has no link-time dependency on NCCL.
+#include <dlfcn.h>
+
+#include <thread>
+
+namespace {
+
+struct NcclApi {
+  void *lib = nullptr;
+  int (*CommInitAll)(void **comms, int ndev, const int *devlist) = nullptr;
+  int (*CommDestroy)(void *comm) = nullptr;
+  int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm, cudaStream_t st) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err) {
+    if (lib) return true;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("MJP_REDUCE_NCCL: cannot load libnccl.so.2: ") + dlerror(); return false; }
+    auto sym = [&](const char *n) { return dlsym(lib, n); };
+    CommInitAll = (decltype(CommInitAll))sym("ncclCommInitAll");
+    CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+    GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+    GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+    if (!CommInitAll || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd) {
+      err = "MJP_REDUCE_NCCL: libnccl lacks a required symbol";
+      return false;
+    }
+    return true;
+  }
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (stable across NCCL 2.x)
+
+thread_local std::string g_multi_create_error;
+
+}  // namespace
+
+struct mjp_multi {
+  std::vector<mjp_handle *> h;
+  std::vector<int> dev;
+  int reduce = MJP_REDUCE_PEER;
+  NcclApi nccl;
+  std::vector<void *> comms;
+  DevBuf d_stage, d_total;        // on device dev[0]: [G][len] gathered vectors, [len] their sum
+  std::vector<DevBuf> d_red;      // NCCL: per-device receive buffer
+  cudaEvent_t r0 = nullptr, r1 = nullptr;
+  float last_ms = 0.f, reduce_ms = 0.f;
+  std::string err;
+};
+
+extern "C" {
+
+int mjp_multi_create(const mjp_multi_config *cfg, mjp_multi **out) {
+  if (!out) return MJP_ERR_INVALID;
+  *out = nullptr;
+  int visible = mjp_device_count();
+  const int G = (cfg && cfg->n_devices > 0) ? cfg->n_devices : visible;
+  if (G < 1) { g_multi_create_error = "mjp_multi_create: no CUDA device"; return MJP_ERR_CUDA; }
+  mjp_multi *m = new (std::nothrow) mjp_multi();
+  if (!m) return MJP_ERR_NOMEM;
+  m->reduce = cfg ? cfg->reduce : MJP_REDUCE_PEER;
+  for (int g = 0; g < G; ++g) {
+    const int d = (cfg && cfg->devices) ? cfg->devices[g] : g;
+    mjp_config c{d, cfg ? cfg->flags : 0, 0};
+    mjp_handle *h = nullptr;
+    int rc = (d >= 0 && d < visible) ? mjp_create(&c, &h) : MJP_ERR_INVALID;
+    if (rc != MJP_OK) {
+      g_multi_create_error = rc == MJP_ERR_INVALID ? "mjp_multi_create: device ordinal out of range" : mjp_last_error(nullptr);
+      mjp_multi_destroy(m);
+      return rc;
+    }
+    m->h.push_back(h); m->dev.push_back(d);
+  }
+  cudaSetDevice(m->dev[0]);
+  cudaEventCreate(&m->r0); cudaEventCreate(&m->r1);
+  if (m->reduce == MJP_REDUCE_NCCL) {
+    if (!m->nccl.load(g_multi_create_error)) { mjp_multi_destroy(m); return MJP_ERR_UNSUPPORTED; }
+    m->comms.assign(G, nullptr);
+    const int rc = m->nccl.CommInitAll(m->comms.data(), G, m->dev.data());
+    if (rc != 0) {
+      g_multi_create_error = std::string("ncclCommInitAll: ") + (m->nccl.GetErrorString ? m->nccl.GetErrorString(rc) : "error");
+      m->comms.clear();
+      mjp_multi_destroy(m);
+      return MJP_ERR_CUDA;
+    }
+    m->d_red.resize(G);
+  } else if (m->reduce != MJP_REDUCE_PEER) {
+    g_multi_create_error = "mjp_multi_create: unknown reduce kind";
+    mjp_multi_destroy(m);
+    return MJP_ERR_INVALID;
+  } else {
+    for (int g = 1; g < G; ++g) {                 // device 0 reads its peers directly when the link allows it
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, m->dev[0], m->dev[g]);
+      if (can) { cudaSetDevice(m->dev[0]); cudaDeviceEnablePeerAccess(m->dev[g], 0); }
+    }
+    cudaGetLastError();                           // (already enabled is not an error worth keeping)
+  }
+  *out = m;
+  return MJP_OK;
+}
+
+void mjp_multi_destroy(mjp_multi *m) {
+  if (!m) return;
+  for (size_t g = 0; g < m->comms.size(); ++g) if (m->comms[g]) m->nccl.CommDestroy(m->comms[g]);
+  for (size_t g = 0; g < m->d_red.size(); ++g) { cudaSetDevice(m->dev[g]); m->d_red[g].release(); }
+  if (!m->dev.empty()) {
+    cudaSetDevice(m->dev[0]);
+    m->d_stage.release(); m->d_total.release();
+    if (m->r0) cudaEventDestroy(m->r0);
+    if (m->r1) cudaEventDestroy(m->r1);
+  }
+  for (mjp_handle *h : m->h) mjp_destroy(h);
+  delete m;
+}
+
+const char *mjp_multi_last_error(const mjp_multi *m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
+
+int mjp_multi_device_count(const mjp_multi *m) { return m ? (int)m->h.size() : 0; }
+
+int mjp_multi_run(mjp_multi *m, const mjp_line_desc *line, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *stats) {
+  if (!m || !line || !rng) return MJP_ERR_INVALID;
+  if (n_inst == 0) { m->err = "n_inst must be >= 1"; return MJP_ERR_INVALID; }
+  const int G = (int)m->h.size();
+  const uint64_t per = (n_inst + G - 1) / G;           // ceil(n/G) contiguous instance ids per device
+  std::vector<int> rc(G, MJP_OK);
+  std::vector<uint64_t> lo(G), cnt(G);
+  for (int g = 0; g < G; ++g) {
+    lo[g] = std::min<uint64_t>((uint64_t)g * per, n_inst);
+    cnt[g] = std::min<uint64_t>(lo[g] + per, n_inst) - lo[g];
+  }
+  // per device: upload its window, run, copy its columns of the per-instance planes back (no aggregate yet)
+  mjp_stats_out planes{};
+  if (stats) { planes = *stats; planes.aggregate = nullptr; }
+  auto work = [&](int g) {
+    if (!cnt[g]) return;
+    mjp_handle *h = m->h[g];
+    int r = upload_impl(h, line, cnt[g], lo[g], n_inst);
+    mjp_rng_spec rg = *rng;
+    rg.first_instance_id = rng->first_instance_id + lo[g];
+    if (r == MJP_OK) r = mjp_launch(h, &rg, 0);
+    if (r == MJP_OK) r = mjp_sync(h);
+    if (r == MJP_OK && stats) r = download_impl(h, &planes, nullptr, lo[g], n_inst);
+    rc[g] = r;
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g) th.emplace_back(work, g);
+  work(0);
+  for (auto &t : th) t.join();
+  m->last_ms = 0.f;
+  for (int g = 0; g < G; ++g) {
+    if (rc[g] != MJP_OK) { m->err = std::string("device ") + std::to_string(m->dev[g]) + ": " + mjp_last_error(m->h[g]); return rc[g]; }
+    if (cnt[g]) m->last_ms = std::max(m->last_ms, m->h[g]->last_ms);
+  }
+  // ---- the one collective: sum of the aggregate vectors ----
+  const int len = mjp_aggregate_len(line->M);
+  const size_t bytes = (size_t)len * 8;
+  int used = 0;
+  for (int g = 0; g < G; ++g) used += cnt[g] != 0;
+  mjp_handle *h0 = m->h[0];
+  auto cuda_fail = [&](cudaError_t e, const char *what) { m->err = std::string(what) + ": " + cudaGetErrorString(e); return MJP_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = cudaSetDevice(m->dev[0])) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const double *result = nullptr;
+  if (m->reduce == MJP_REDUCE_NCCL) {
+    for (int g = 0; g < G; ++g) {
+      cudaSetDevice(m->dev[g]);
+      if ((e = m->d_red[g].reserve(bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+      if (!cnt[g]) {                                   // an empty shard contributes zeros
+        if ((e = m->h[g]->d_agg.reserve(bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        cudaMemsetAsync(m->h[g]->d_agg.ptr, 0, bytes, m->h[g]->stream);
+      }
+    }
+    cudaSetDevice(m->dev[0]);
+    cudaEventRecord(m->r0, h0->stream);
+    m->nccl.GroupStart();
+    int nrc = 0;
+    for (int g = 0; g < G; ++g) {
+      cudaSetDevice(m->dev[g]);
+      const int r = m->nccl.AllReduce(m->h[g]->d_agg.ptr, m->d_red[g].ptr, (size_t)len, kNcclFloat64, kNcclSum, m->comms[g],
+                                      m->h[g]->stream);
+      if (r) nrc = r;
+    }
+    const int r2 = m->nccl.GroupEnd();
+    if (nrc || r2) { m->err = std::string("ncclAllReduce: ") + (m->nccl.GetErrorString ? m->nccl.GetErrorString(nrc ? nrc : r2) : "error"); return MJP_ERR_CUDA; }
+    cudaSetDevice(m->dev[0]);
+    cudaEventRecord(m->r1, h0->stream);
+    for (int g = 0; g < G; ++g) { cudaSetDevice(m->dev[g]); if ((e = cudaStreamSynchronize(m->h[g]->stream)) != cudaSuccess) return cuda_fail(e, "ncclAllReduce"); }
+    cudaSetDevice(m->dev[0]);
+    result = m->d_red[0].as<double>();
+  } else {
+    if ((e = m->d_stage.reserve(bytes * G)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = m->d_total.reserve(bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaEventRecord(m->r0, h0->stream);
+    int rows = 0;
+    for (int g = 0; g < G; ++g) {
+      if (!cnt[g]) continue;
+      e = cudaMemcpyPeerAsync((char *)m->d_stage.ptr + bytes * rows, m->dev[0], m->h[g]->d_agg.ptr, m->dev[g], bytes, h0->stream);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyPeerAsync");
+      ++rows;
+    }
+    mjp::mjp_aggregate_final<<<(len + 127) / 128, 128, 0, h0->stream>>>(m->d_stage.as<double>(), rows, len, m->d_total.as<double>());
+    cudaEventRecord(m->r1, h0->stream);
+    if ((e = cudaStreamSynchronize(h0->stream)) != cudaSuccess) return cuda_fail(e, "aggregate sum");
+    result = m->d_total.as<double>();
+  }
+  cudaEventElapsedTime(&m->reduce_ms, m->r0, m->r1);
+  if (stats && stats->aggregate) {
+    if ((e = cudaMemcpy(stats->aggregate, result, bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  }
+  (void)used;
+  return MJP_OK;
+}
+
+int mjp_multi_last_ms(mjp_multi *m, float *kernel_ms_max, float *reduce_ms) {
+  if (!m) return MJP_ERR_INVALID;
+  if (kernel_ms_max) *kernel_ms_max = m->last_ms;
+  if (reduce_ms) *reduce_ms = m->reduce_ms;
   return MJP_OK;
 }
 

@@ -156,14 +156,14 @@ __device__ __forceinline__ bool end_time_resume(double t_up, double t_down, doub
 #define MJP_NOINLINE __noinline__
 #endif
 // sojourn of COUNTER mode: Erlang-2 from one Philox block {idx, consumer, gid}
-__device__ MJP_NOINLINE double sojourn_counter(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate) {
+static __device__ MJP_NOINLINE double sojourn_counter(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate) {
   uint32_t o[4];
   philox4x32_10(idx, consumer, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
   return __ddiv_rn(-det_log(__dmul_rn(u52open(o[0], o[1]), u52open(o[2], o[3]))), rate);
 }
 // sojourn of REPLAY / TAPE mode: the literal loop of core.clj:185-191; e is the cursor of the exponential
 // stream.  tu/te != nullptr: the draws are read from this machine's tapes (NaN once a tape is exhausted).
-__device__ MJP_NOINLINE double sojourn_replay(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate,
+static __device__ MJP_NOINLINE double sojourn_replay(uint32_t idx, uint32_t consumer, uint64_t gid, uint64_t seed, double rate,
                                              uint32_t *e_io, const double *tu, const double *te, uint32_t len_u,
                                              uint32_t len_e) {
   uint32_t o[4], e = *e_io;
@@ -191,7 +191,7 @@ __device__ MJP_NOINLINE double sojourn_replay(uint32_t idx, uint32_t consumer, u
   return T;
 }
 // the two uniforms of job-type block `blk` (consumer 0)
-__device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid, uint64_t seed, double *u0, double *u1) {
+static __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid, uint64_t seed, double *u0, double *u1) {
   uint32_t o[4];
   philox4x32_10(blk, 0u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
   *u0 = u53(o[0], o[1]); *u1 = u53(o[2], o[3]);
@@ -978,77 +978,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #undef LASTCLK
 #undef FUT_N
 #undef STARTED
-}
-
-// ---- aggregate: calc-basics (core.clj:617-634) per instance, then sum(x), sum(x^2) -------------
-// One block-wide tree per metric; partials[block][metric] are summed in a fixed
-// order by mjp_aggregate_final, so the result does not depend on scheduling.
-__global__ void mjp_aggregate_partial(const KParams p, double *partials, int n_metrics) {
-  extern __shared__ double red[];      // [2][blockDim]
-  const int tid = threadIdx.x, nt = blockDim.x, M = p.M;
-  const uint64_t n = p.n_inst;
-  const double run_time = p.run_to - p.warm_up;
-  for (int metric = -1; metric < n_metrics; ++metric) {
-    double s1 = 0.0, s2 = 0.0;
-    for (uint64_t g = (uint64_t)blockIdx.x * nt + tid; g < n; g += (uint64_t)gridDim.x * nt) {
-      if (p.status[g] != MJP_INST_NORMAL_END) continue;
-      double x;
-      if (metric < 0) x = 1.0;
-      else if (metric == 0) x = (double)p.njobs[g] / run_time;
-      else if (metric == 1) x = p.njobs[g] ? p.residence[g] / (double)p.njobs[g] : 0.0;
-      else if (metric < 2 + M) x = p.blocked[(size_t)(metric - 2) * n + g] / run_time;
-      else if (metric < 2 + 2 * M) x = p.starved[(size_t)(metric - 2 - M) * n + g] / run_time;
-      else {
-        const int b = metric - 2 - 2 * M;
-        const int lv = p.lvl[b], cap = p.N[b];
-        double acc = 0.0;
-        for (int k = 0; k <= cap; ++k) acc = acc + (double)k * p.occ[(size_t)(lv + k) * n + g];
-        x = acc / run_time;
-      }
-      s1 += x; s2 += x * x;
-    }
-    red[tid] = s1; red[nt + tid] = s2;
-    __syncthreads();
-    for (int off = nt >> 1; off > 0; off >>= 1) {
-      if (tid < off) { red[tid] += red[tid + off]; red[nt + tid] += red[nt + tid + off]; }
-      __syncthreads();
-    }
-    if (tid == 0) {
-      const int slot = (metric < 0) ? 0 : 1 + 2 * metric;
-      double *row = partials + (size_t)blockIdx.x * (1 + 2 * n_metrics);
-      row[slot] = red[0];
-      if (metric >= 0) row[slot + 1] = red[nt];
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void mjp_aggregate_final(const double *partials, int n_blocks, int len, double *out) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= len) return;
-  double s = 0.0;
-  for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * len + q];
-  out[q] = s;
-}
-
-// ---- probe: end-time (core.clj:138-151) over a literal :up&down schedule ------------------------
-__global__ void mjp_end_time_probe(const uint8_t *kinds, const double *times, int n, double clock, double dur,
-                                   double *out) {
-  if (blockIdx.x || threadIdx.x) return;
-  const double QNAN = __longlong_as_double(0x7FF8000000000000ll);
-  int k = 0;
-  while (k < n && times[k] < clock) ++k;                     // drop-while core.clj:143
-  if (k >= n) { *out = QNAN; return; }
-  double v;
-  bool pending;
-  if (kinds[k] == 1) { pending = end_time_begin(true, times[k], clock, dur, v); ++k; }   // :future is :down
-  else pending = end_time_begin(false, 0.0, clock, dur, v);
-  while (pending) {                                          // k is at the next :up event
-    if (k + 1 >= n) { v = QNAN; break; }
-    pending = end_time_resume(times[k], times[k + 1], v, v);
-    k += 2;
-  }
-  *out = v;
 }
 
 }  // namespace mjp

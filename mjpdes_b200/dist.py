@@ -88,10 +88,12 @@ def run_sharded(line: abi.HostLine, n_total: int, mode: int = abi.RNG_COUNTER, s
 
             from . import engine
             dev = torch.cuda.current_device() if device is None else device
+            dev = torch.device(dev).index if not isinstance(dev, int) else dev
+            device = torch.device("cuda", int(dev))
             with engine.Handle(device=int(dev)) as h:
                 local = h.run(shard, hi - lo, mode=mode, seed=seed, first_instance_id=first_instance_id + lo).stats
         else:
             local = runner(shard, hi - lo, mode, seed, first_instance_id + lo)
         agg = np.array(local.aggregate, dtype=np.float64)
-    total = all_reduce_sum(agg, group=group)
+    total = all_reduce_sum(agg, group=group, device=device)
     return ShardResult(lo, hi, local, total, summarize_aggregate(total, line))

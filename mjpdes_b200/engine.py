@@ -160,6 +160,22 @@ class Handle:
         self._check(self._lib.mjp_last_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def device_aggregate(self) -> tuple[int, int]:
+        """(device address, length in doubles) of the aggregate vector of the last launch; valid after ``sync``."""
+        p, n = C.POINTER(C.c_double)(), C.c_int32(0)
+        self._check(self._lib.mjp_device_aggregate(self._h, C.byref(p), C.byref(n)))
+        return C.cast(p, C.c_void_p).value, int(n.value)
+
+    def aggregate_tensor(self):
+        """The aggregate vector of the last launch as a torch CUDA tensor that ALIASES the library's buffer (no
+        copy): what a multi-process host hands to ``torch.distributed.all_reduce`` (NCCL) after ``sync``."""
+        import torch
+        addr, n = self.device_aggregate()
+
+        class _Blob:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (addr, False), "version": 2}
+        return torch.as_tensor(_Blob(), device=torch.device("cuda", self.device))
+
     def probe_end_time(self, kinds, times, clock: float, dur: float) -> float:
         k = np.ascontiguousarray(kinds, np.uint8)
         t = np.ascontiguousarray(times, np.float64)
@@ -167,3 +183,46 @@ class Handle:
         self._check(self._lib.mjp_probe_end_time(self._h, abi.ptr(k, C.c_uint8), abi.ptr(t, C.c_double), len(k),
                                                  clock, dur, C.byref(out)))
         return float(out.value)
+
+
+class MultiHandle:
+    """All (or the named) GPUs of one box behind one call: ``mjp_multi_run`` shards the batch into contiguous
+    ranges of instance ids, one host thread and one stream per device, and sums the aggregate vectors on the
+    devices (peer copies over NVLink, or NCCL).  The fan-out of ``main-loop-multi`` (core.clj:746-766)."""
+
+    def __init__(self, devices=None, event_hash: bool = False, reduce: int = abi.REDUCE_PEER):
+        self._lib = abi.load_library()
+        devs = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        cfg = abi.MultiConfig(0 if devs is None else len(devs), abi.ptr(devs, C.c_int32),
+                              abi.CFG_EVENT_HASH if event_hash else 0, int(reduce))
+        self._m = C.c_void_p()
+        rc = self._lib.mjp_multi_create(C.byref(cfg), C.byref(self._m))
+        if rc != abi.OK:
+            raise abi.MjpError(rc, (self._lib.mjp_multi_last_error(None) or b"").decode())
+        self.n_devices = int(self._lib.mjp_multi_device_count(self._m))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.mjp_multi_destroy(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def run(self, line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int = 0,
+            first_instance_id: int = 0, stats: abi.HostStats | None = None) -> RunResult:
+        n = int(n_inst)
+        stats = stats or abi.HostStats(line, n)
+        rng = abi.RngSpec(mode, 0, seed, first_instance_id)
+        desc, st = line.desc(), stats.struct()
+        rc = self._lib.mjp_multi_run(self._m, C.byref(desc), n, C.byref(rng), C.byref(st))
+        if rc != abi.OK:
+            raise abi.MjpError(rc, (self._lib.mjp_multi_last_error(self._m) or b"").decode())
+        k, r = C.c_float(0), C.c_float(0)
+        self._lib.mjp_multi_last_ms(self._m, C.byref(k), C.byref(r))
+        res = RunResult(line, stats, None, rc, float(k.value), 3 * self.n_devices + 1)
+        res.reduce_ms = float(r.value)
+        return res

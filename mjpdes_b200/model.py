@@ -378,11 +378,21 @@ def main_loop(model: dict, handle=None, out_stream=None, seed: int = DEFAULT_SEE
     h = handle or engine.Handle(device=0)
     try:
         if cl.host.log:
-            if log_capacity is None:
-                ml = cl.host.max_lines
-                per = (ml + 4 * cl.host.M) if ml != abi.UINT64_MAX else int(4.0 * cl.host.M * cl.host.run_to) + 1024
+            fixed = log_capacity is not None
+            if not fixed:
+                # :max-lines is tested per TICK (util/log.clj:220-226), so an instance can overshoot it by one
+                # tick: at most 9 messages per machine plus the entry/exit extras (the device's staging bound)
+                ml, tick = cl.host.max_lines, 9 * cl.host.M + 4
+                per = (ml + tick) if ml != abi.UINT64_MAX else int(4.0 * cl.host.M * cl.host.run_to) + 1024
                 log_capacity = max(1024, min(per * n, 1 << 27))
-            res = h.run(cl.host, n, mode=mode, seed=seed, log_capacity=log_capacity)
+            while True:
+                res = h.run(cl.host, n, mode=mode, seed=seed, log_capacity=log_capacity)
+                if res.rc != abi.LOG_TRUNCATED:
+                    break
+                # never hand back a log with silent holes: the run is deterministic, so repeat it with more room
+                if fixed or log_capacity >= (1 << 31):
+                    raise abi.MjpError(res.rc, f"SCADA record buffer too small ({log_capacity} records)")
+                log_capacity *= 4
         else:
             res = h.run(cl.host, n, mode=mode, seed=seed)
     finally:

@@ -19,7 +19,7 @@ _LIB = None
 def build():
     deps = [os.path.join(_HERE, f) for f in ("hostsim.cpp", "cuda_shim.h")] + [
         os.path.join(_ROOT, "mjpdes_b200", "csrc", f)
-        for f in ("mjp_line_kernel.cuh", "mjp_device.cuh", "mjp_params.h", "mjp_plan.h")] + [
+        for f in ("mjp_line_kernel.cuh", "mjp_aux_kernels.cuh", "mjp_device.cuh", "mjp_params.h", "mjp_plan.h")] + [
         os.path.join(_ROOT, "include", "mjpdes_b200.h")]
     if (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB_PATH,

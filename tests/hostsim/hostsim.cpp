@@ -1,7 +1,7 @@
 // hostsim.cpp -- TEST-ONLY host execution of the kernel source (see cuda_shim.h).
 #include "cuda_shim.h"
 #define MJP_FIXED_NT 1        /* the shim runs one thread per block */
-#include "../../mjpdes_b200/csrc/mjp_line_kernel.cuh"
+#include "../../mjpdes_b200/csrc/mjp_aux_kernels.cuh"
 #include "../../mjpdes_b200/csrc/mjp_plan.h"
 
 #include <limits>

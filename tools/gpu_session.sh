@@ -1,0 +1,42 @@
+#!/bin/bash
+# One gpurun session: GPU tests, bench, ncu captures.  Usage: tools/gpu_session.sh <tag> [steps...]
+# steps: tests bench ncu_c2 ncu_wide ncu_scada dram launches
+TAG=$1; shift
+STEPS="$*"
+O=gpurun_out
+mkdir -p $O
+has() { [[ " $STEPS " == *" $1 "* ]]; }
+NCU="ncu --set full --clock-control none --import-source on -k regex:mjp_line_kernel --launch-skip 1 --launch-count 1"
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $O/${TAG}_gpu.txt 2>&1
+if has tests; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_tests.log 2>&1; echo "tests exit $?" >> $O/${TAG}_tests.log
+  tail -5 $O/${TAG}_tests.log
+fi
+if has bench; then
+  timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench exit $?"
+  tail -c 600 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err
+fi
+if has benchq; then
+  timeout 600 python bench.py --skip-configs > $O/${TAG}_benchq.json 2> $O/${TAG}_benchq.err; echo "benchq exit $?"
+  tail -c 400 $O/${TAG}_benchq.json; tail -3 $O/${TAG}_benchq.err
+fi
+prof() {   # name
+  timeout 600 python tools/profile_config.py $1 --out $O/${TAG}_$1_events.json > $O/${TAG}_$1_plain.log 2>&1 || { echo "$1 plain run failed"; tail -3 $O/${TAG}_$1_plain.log; return; }
+  cat $O/${TAG}_$1_events.json; echo
+  timeout 900 $NCU -f -o $O/${TAG}_$1 python tools/profile_config.py $1 > $O/${TAG}_$1_ncu.log 2>&1; echo "ncu $1 exit $?"
+}
+if has ncu_c2; then prof C2_example; fi
+if has ncu_wide; then prof C3_sweep10; prof C4_mixed20_stats_many; prof C5_long50; fi
+if has ncu_c4; then prof C4_mixed20_stats; fi
+if has ncu_slice; then prof C5_long50_slice; fi
+if has ncu_scada; then prof C4_mixed20_scada; prof example_scada; fi
+if has dram; then
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k regex:mjp_line_kernel --launch-skip 1 --launch-count 1 --csv --log-file $O/${TAG}_dram_c2full.csv \
+    python tools/profile_config.py C2_example_full > $O/${TAG}_dram.log 2>&1; echo "dram exit $?"
+fi
+if has launches; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --skip-configs --no-cpu-baseline > $O/${TAG}_launches.log 2>&1; echo "launches exit $?"
+fi
+ls -la $O | tail -30

@@ -11,8 +11,13 @@ import csv, os, re, subprocess, sys, tempfile
 def line_map(so, mangled):
     d = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout
+    # one cubin per translation unit (mjp_variant.cu is compiled once per kernel family): find the kernel's
+    txt = ""
+    for cub in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):
+        syms = subprocess.run(["cuobjdump", "-elf", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout
+        if ".text." + mangled in syms:
+            txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout
+            break
     out, cur, on = [], (None, 0), False
     for ln in txt.splitlines():
         if ln.startswith("//--------------------- .text."):
