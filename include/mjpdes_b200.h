@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MJP_ABI_VERSION 1
+#define MJP_ABI_VERSION 2
 
 /* ---- call status ------------------------------------------------------- */
 enum {
@@ -109,6 +109,12 @@ typedef struct mjp_line_desc {
   const double  *W_inst;       /* [M][n_inst]   */
   const int32_t *N_inst;       /* [M-1][n_inst] */
   const double  *w_inst;       /* [K*M][n_inst] */
+  /* Optional: group_rank[i] = position of machine i's NAME among the machine names in Clojure hash-map
+   * iteration order.  clean-log-buf regroups a tick's messages with (group-by :m ...) (util/log.clj:44), whose
+   * result iterates in insertion order up to 8 machines and in keyword-hash order from the 9th on, so the
+   * order is only needed for ticks in which MORE than 8 machines log.  Must be a permutation of 0..M-1.
+   * NULL = the names :m1 .. :mM of the reference's models (resources/example.clj etc.), ranked by the library.            */
+  const int32_t *group_rank;   /* [M] */
 } mjp_line_desc;
 
 /* ---- random numbers ------------------------------------------------------ */

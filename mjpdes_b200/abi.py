@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # call status
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, LOG_TRUNCATED = range(6)
@@ -57,6 +57,7 @@ class LineDesc(C.Structure):
         ("jm2dm", C.c_uint8), ("log", C.c_uint8), ("up_down", C.c_uint8), ("reserved0", C.c_uint8),
         ("reserved1", C.c_uint32), ("max_lines", C.c_uint64),
         ("lam_inst", _pd), ("mu_inst", _pd), ("W_inst", _pd), ("N_inst", _pi32), ("w_inst", _pd),
+        ("group_rank", _pi32),
     ]
 
 
@@ -139,7 +140,7 @@ class HostLine:
 
     def __init__(self, lam, mu, W, discipline, N, portion, w, warm_up, run_to, run_to_job=-1,
                  jm2dm=False, log=False, up_down=False, max_lines=0,
-                 lam_inst=None, mu_inst=None, W_inst=None, N_inst=None, w_inst=None):
+                 lam_inst=None, mu_inst=None, W_inst=None, N_inst=None, w_inst=None, group_rank=None):
         f8 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         self.lam, self.mu, self.W = f8(lam), f8(mu), f8(W)
         self.discipline = np.ascontiguousarray(discipline, dtype=np.uint8)
@@ -156,6 +157,8 @@ class HostLine:
         self.max_lines = int(max_lines)
         self.lam_inst, self.mu_inst, self.W_inst, self.w_inst = f8(lam_inst), f8(mu_inst), f8(W_inst), f8(w_inst)
         self.N_inst = None if N_inst is None else np.ascontiguousarray(N_inst, dtype=np.int32)
+        # hash-map rank of the machine names (util/log.clj:44 for ticks with > 8 machines); None = :m1 .. :mM
+        self.group_rank = None if group_rank is None else np.ascontiguousarray(group_rank, dtype=np.int32)
         assert self.mu.shape == (self.M,) and self.W.shape == (self.M,) and self.discipline.shape == (self.M,)
         assert self.N.shape == (max(self.M - 1, 0),)
 
@@ -180,6 +183,7 @@ class HostLine:
         d.lam_inst, d.mu_inst = ptr(self.lam_inst, C.c_double), ptr(self.mu_inst, C.c_double)
         d.W_inst, d.w_inst = ptr(self.W_inst, C.c_double), ptr(self.w_inst, C.c_double)
         d.N_inst = ptr(self.N_inst, C.c_int32)
+        d.group_rank = ptr(self.group_rank, C.c_int32)
         return d
 
 

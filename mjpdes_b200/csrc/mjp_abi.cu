@@ -110,6 +110,14 @@ static int validate(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst, uint
   if (!(L->warm_up >= 0.0) || !std::isfinite(L->warm_up)) return fail(h, MJP_ERR_INVALID, ":warm-up-time must be non-negative and finite (core.clj:104)");
   // +inf is allowed here (main-loop-continuous never ends, core.clj:801-843); mjp_launch_slice refuses to run it unsliced
   if (!(L->run_to > 0.0)) return fail(h, MJP_ERR_INVALID, ":run-to-time must be positive (core.clj:105)");
+  if (L->group_rank) {
+    uint64_t seen = 0;
+    for (int i = 0; i < L->M; ++i) {
+      const int r = L->group_rank[i];
+      if (r < 0 || r >= L->M || ((seen >> r) & 1)) return fail(h, MJP_ERR_INVALID, "group_rank must be a permutation of 0..M-1");
+      seen |= 1ull << r;
+    }
+  }
   // per-instance planes are [rows][n_total]; this call covers columns lo .. lo + n_inst
   auto plane_ok = [&](const double *pl, int rows, bool allow_zero) {
     for (int r = 0; r < rows; ++r)
@@ -235,15 +243,17 @@ static int upload_impl(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst, u
 
   // ---- constants: lam mu W w dur thr | N lvl ----
   const size_t dbytes = pl.cd.size() * sizeof(double), ibytes = pl.ci.size() * sizeof(int32_t);
-  CK(h->d_const.reserve(dbytes + ibytes));
+  CK(h->d_const.reserve(dbytes + ibytes + pl.by_rank.size()));
   CK(cudaMemcpyAsync(h->d_const.ptr, pl.cd.data(), dbytes, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync((char *)h->d_const.ptr + dbytes, pl.ci.data(), ibytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync((char *)h->d_const.ptr + dbytes + ibytes, pl.by_rank.data(), pl.by_rank.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));   // pl is stack-owned
   const double *dc = h->d_const.as<double>();
   kp.lam = dc + pl.off_lam(); kp.mu = dc + pl.off_mu(); kp.W = dc + pl.off_W(); kp.w = dc + pl.off_w();
   kp.dur = dc + pl.off_dur(); kp.thr = dc + pl.off_thr();
   kp.N = reinterpret_cast<const int32_t *>((const char *)h->d_const.ptr + dbytes);
   kp.lvl = kp.N + (M - 1);
+  kp.by_rank = reinterpret_cast<const uint8_t *>((const char *)h->d_const.ptr + dbytes + ibytes);
 
   // ---- per-instance planes ----
   const size_t pM = align_up(n_inst * M * sizeof(double), 256), pKM = align_up(n_inst * (size_t)K * M * sizeof(double), 256);
@@ -601,9 +611,14 @@ struct NcclApi {
   const char *(*GetErrorString)(int) = nullptr;
   bool load(std::string &err) {
     if (lib) return true;
+    // 1. the NCCL the host process has loaded already (a JVM or Python host that uses NCCL itself -- e.g. torch's
+    //    bundled copy -- must not get a second, different libnccl.so.2 mapped under the same soname);
+    // 2. the path in $MJP_NCCL_LIB;  3. the loader's default libnccl.so.2.  Symbols stay private (RTLD_LOCAL).
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+    if (!lib) if (const char *path = std::getenv("MJP_NCCL_LIB")) lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (lib) break;
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     if (!lib) { err = std::string("MJP_REDUCE_NCCL: cannot load libnccl.so.2: ") + dlerror(); return false; }
     auto sym = [&](const char *n) { return dlsym(lib, n); };

@@ -97,13 +97,21 @@ __device__ __forceinline__ int put_record(const LogTick &t, int q, unsigned long
 // machine the classes in order of first appearance, within a class the original order; a machine's :bl/:ub
 // (:st/:us) are dropped iff exactly two (masks two_b / two_s).  Out of line: ticks that are not already in
 // this order are the exception.  Returns records written | dropped << 16 | mismatch << 31.
+// by_rank != nullptr: more than 8 machines logged in this tick, so the groups come in hash-map order of the
+// machine names (by_rank[0..M) = machines in that order) instead of first appearance.
 template <typename MaskT>
 __device__ __noinline__ unsigned emit_general(const LogTick t, const unsigned long long *stage, int ns, MaskT two_b,
-                                              MaskT two_s) {
+                                              MaskT two_s, const uint8_t *by_rank, int M) {
   unsigned q = 0, dropped = 0, bad = 0;
   MaskT done_m = 0;                                          // machines whose group has been written
-  for (int a = 0; a < ns; ++a) {
-    const unsigned m = (unsigned)(stage[a] >> 8) & 0xFFu;
+  for (int a0 = 0; a0 < (by_rank ? M : ns); ++a0) {
+    int a = a0;
+    unsigned m;
+    if (by_rank) {
+      m = by_rank[a0];
+      for (a = 0; a < ns && ((unsigned)(stage[a] >> 8) & 0xFFu) != m; ++a) {}
+      if (a == ns) continue;                                 // this machine logged nothing in the tick
+    } else m = (unsigned)(stage[a] >> 8) & 0xFFu;
     const MaskT mbit = (MaskT)1 << m;
     if (done_m & mbit) continue;
     done_m |= mbit;
@@ -422,18 +430,19 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   };
   // buf+ / buf- (util/log.clj:159-171): of the messages a tick puts on a buffer, the FIRST IN CLEANED ORDER
   // gets the elapsed time at its level n, the others add (clk - clk) = 0.  A buffer sees at most one :bj (from
-  // machine b) and one :sm (from machine b+1) per tick; cleaned order is by machine in order of first
-  // appearance (util/log.clj:44), so when both occur the winner is decided by `lead`.  The winning level is
-  // kept in bits 8-15 of the count word; bit 16 = first message was the :bj, bit 17 = one message so far,
-  // bit 18 = two.  Stale bits of an older tick are overwritten by the first message of a new one.
-  auto buffer_tick_bits = [&](uint32_t w, MaskT bbit, int n, bool is_bj, bool precedes) -> uint32_t {
+  // machine b) and one :sm (from machine b+1) per tick; cleaned order is by machine -- in order of first
+  // appearance while at most 8 machines log in the tick, in hash-map order of the machine names beyond
+  // (group-by :m, util/log.clj:44) -- so when both occur the winner is only known when the tick is complete.
+  // Kept in the count word: bits 8-15 the level of the FIRST message, bit 16 = it was the :bj, bit 17 = one
+  // message so far, bit 18 = two (the second one's level follows: a :sm after a :bj sees one job more, a :bj
+  // after a :sm one less).  Stale bits of an older tick are overwritten by the first message of a new one.
+  auto buffer_tick_bits = [&](uint32_t w, MaskT bbit, int n, bool is_bj) -> uint32_t {
     if (!(touched & bbit)) {
       touched |= bbit;
       return (w & 0xFF000000u) | ((uint32_t)n << 8) | (is_bj ? 0x10000u : 0u) | 0x20000u;
     }
-    uint32_t hi = w & 0xFFFFFF00u;
+    const uint32_t hi = w & 0xFFFFFF00u;
     if ((((hi >> 16) & 1u) != 0) == is_bj || (hi & 0x40000u)) flags |= F_OVF;   // same kind twice, or a third message
-    if (precedes) hi = (hi & 0xFFFF00FFu) | ((uint32_t)n << 8);
     return hi | 0x40000u;
   };
   auto toggle = [&](MaskT &par, MaskT &two, MaskT bit) {
@@ -509,8 +518,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     // slots).
     MaskT gdone = 0;
     unsigned cdone = 0, pm = 0xFFFFFFFFu, pc = 3u;
-    bool grouped = true;
-    for (int x = 0; __any_sync(fm, x < ns); ++x) if (x < ns) {
+    // (a tick in which more than 8 machines logged is regrouped in hash-map order: general routine)
+    const bool wide = MT == 0 && MO::popc(seen) > 8;
+    bool grouped = !wide;
+    for (int x = 0; __any_sync(fm, !wide && x < ns); ++x) if (!wide && x < ns) {
       const unsigned long long w = g_stage[x];
       const unsigned act = (unsigned)w & 0xFFu, m = (unsigned)(w >> 8) & 0xFFu, c = log_class(act);
       const MaskT mbit = MJP_BIT(m);
@@ -521,8 +532,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       dropped += r == 1; if (r == 2) flags |= F_OVF;
       ++q;
     }
-    if (!grouped) {
-      const unsigned r = emit_general<MaskT>(lt, g_stage, ns, twoB, twoS);
+    if (!grouped && ns) {
+      const unsigned r = emit_general<MaskT>(lt, g_stage, ns, twoB, twoS, wide ? p.by_rank : nullptr, M);
       q = (int)(r & 0xFFFFu); dropped = (r >> 16) & 0x7FFFu;
       if (r >> 31) flags |= F_OVF;
     }
@@ -567,10 +578,17 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       for (MaskT q = warm ? pB : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, false); }
       for (MaskT q = warm ? pS : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; interval(i, true); }
     }
-    // buf+ / buf-: one RED per touched buffer, at the level recorded by buffer_tick_bits
+    // buf+ / buf-: one RED per touched buffer, at the level recorded by buffer_tick_bits.  When the buffer saw
+    // both a :bj and a :sm, the one whose machine comes first in cleaned order counts (see buffer_tick_bits).
+    const MaskT bj_first = (MT == 0 && MO::popc(seen) > 8) ? (MaskT)p.hlead_mask : lead;
     for (MaskT q = warm ? touched : (MaskT)0; __any_sync(fm, q != 0);) if (q) {
       const int b = MO::ffs(q); q &= q - 1;
-      const int n = (int)((CNT(b) >> 8) & 0xFFu);
+      const uint32_t cw = CNT(b);
+      int n = (int)((cw >> 8) & 0xFFu);
+      if (cw & 0x40000u) {
+        const bool first_bj = (cw & 0x10000u) != 0, bj_wins = ((bj_first >> b) & 1) != 0;
+        n += (first_bj == bj_wins) ? 0 : (first_bj ? 1 : -1);
+      }
       const double lc = LASTCLK(b);
       red_add(p.occ + (size_t)(c_lvl[b] + n) * n_inst + g, tick_clk - lc);
       LASTCLK(b) = tick_clk;
@@ -882,7 +900,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
-        CNT(i) = (uint32_t)(n + 1) | buffer_tick_bits(cw, bit, n, true, ((lead >> i) & 1) != 0);
+        CNT(i) = (uint32_t)(n + 1) | buffer_tick_bits(cw, bit, n, true);
         if (n + 1 == (int)(cw >> 24)) full |= bit;
         empty &= ~(bit << 1);
       } else {
@@ -907,7 +925,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);
       if (LOG) stage_msg(MJP_ACT_SM, i, n, id);
-      CNT(b) = (uint32_t)(n - 1) | buffer_tick_bits(cw, bbit, n, false, ((lead >> b) & 1) == 0);
+      CNT(b) = (uint32_t)(n - 1) | buffer_tick_bits(cw, bbit, n, false);
       if (n - 1 == 0) empty |= bit;
       full &= ~bbit;
       occ |= bit; STARTED(i) = id;

@@ -16,11 +16,13 @@ struct KParams {
   double warm_up, run_to;
   int64_t run_to_job;     // -1 unset
   uint64_t bbs_mask;      // bit i: machine i is :BBS
+  uint64_t hlead_mask;    // bit i: machine i's name precedes machine i+1's in Clojure hash-map order (util/log.clj:44, > 8 groups)
   int32_t jm2dm, up_down, log_on, reserved;
   uint64_t max_lines;
   // shared constants (device pointers)
   const double *lam, *mu, *W, *w, *dur, *thr;   // [M] [M] [M] [K*M] [K*M]=w/W [K]=new-job thresholds
   const int32_t *N, *lvl;                       // [M-1] capacity, [M-1] first level row of buffer b
+  const uint8_t *by_rank;                       // [M] machines in Clojure hash-map order of their names
   // per-instance override planes, instance-fastest (nullptr = absent)
   const double *lam_i, *mu_i, *W_i, *w_i;
   const int32_t *N_i;

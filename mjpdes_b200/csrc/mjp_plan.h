@@ -2,7 +2,9 @@
 // constant table and shared-memory layout ("preprocess-model" for the device,
 // core.clj:578-615).  Pure host C++, no CUDA calls.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <string>
 #include <vector>
 
 #include "../../include/mjpdes_b200.h"
@@ -10,10 +12,46 @@
 
 namespace mjp {
 
+// hasheq of the Clojure keyword :<name> (clojure 1.9: Keyword.hasheq = Symbol.hasheq + 0x9e3779b9, Symbol.hasheq =
+// hashCombine(Murmur3.hashUnencodedChars(name), 0)); names here are ASCII.  Restated from the published Clojure
+// sources; (hash :a) = -2123407586 is the known value it reproduces (tests/test_cljhash.py).
+inline uint32_t clj_keyword_hash(const std::string &name) {
+  auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+  auto mix_k1 = [&](uint32_t k) { k *= 0xcc9e2d51u; k = rotl(k, 15); return k * 0x1b873593u; };
+  uint32_t h = 0;
+  const size_t n = name.size();
+  for (size_t i = 1; i < n; i += 2) {
+    h ^= mix_k1((uint32_t)(unsigned char)name[i - 1] | ((uint32_t)(unsigned char)name[i] << 16));
+    h = rotl(h, 13); h = h * 5u + 0xe6546b64u;
+  }
+  if (n & 1) h ^= mix_k1((uint32_t)(unsigned char)name[n - 1]);
+  h ^= (uint32_t)(2 * n); h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  const uint32_t seed = h;                                               // hashCombine(seed, 0)
+  const uint32_t sym = seed ^ (0u + 0x9e3779b9u + (seed << 6) + (uint32_t)((int32_t)seed >> 2));
+  return sym + 0x9e3779b9u;
+}
+// PersistentHashMap iterates its 32-way trie by ascending 5-bit chunks of the hash, lowest chunk first
+inline uint64_t clj_trie_key(uint32_t h) {
+  uint64_t k = 0;
+  for (int s = 0; s < 35; s += 5) k = (k << 5) | ((h >> s) & 31u);
+  return k;
+}
+// rank[i] of the default machine names :m1 .. :mM in hash-map order
+inline std::vector<int32_t> default_group_rank(int M) {
+  std::vector<int> order(M);
+  std::vector<uint64_t> key(M);
+  for (int i = 0; i < M; ++i) { order[i] = i; key[i] = clj_trie_key(clj_keyword_hash("m" + std::to_string(i + 1))); }
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  std::vector<int32_t> rank(M);
+  for (int pos = 0; pos < M; ++pos) rank[order[pos]] = pos;
+  return rank;
+}
+
 struct LinePlan {
   KParams kp{};                 // everything except device pointers, seed and first_id
   std::vector<double> cd;       // lam[M] mu[M] W[M] w[K*M] dur[K*M] thr[K]
   std::vector<int32_t> ci;      // N[M-1] lvl[M-1]
+  std::vector<uint8_t> by_rank; // [M] machines in hash-map order of their names (util/log.clj:44 beyond 8 groups)
   size_t per_thread_bytes = 0;
 
   // offsets (in doubles) of the sections of cd
@@ -56,6 +94,12 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
   kp.jm2dm = L->jm2dm ? 1 : 0; kp.up_down = L->up_down ? 1 : 0; kp.log_on = L->log ? 1 : 0;
   kp.max_lines = L->max_lines;
   for (int i = 0; i < M; ++i) if (L->discipline[i] == MJP_BBS) kp.bbs_mask |= (1ull << i);
+  {
+    std::vector<int32_t> rank = L->group_rank ? std::vector<int32_t>(L->group_rank, L->group_rank + M) : default_group_rank(M);
+    pl.by_rank.assign(M, 0);
+    for (int i = 0; i < M; ++i) pl.by_rank[rank[i]] = (uint8_t)i;           // (validated to be a permutation)
+    for (int i = 0; i + 1 < M; ++i) if (rank[i] < rank[i + 1]) kp.hlead_mask |= (1ull << i);
+  }
   int sumN = 0, levels = 0;
   pl.ci.assign(L->N, L->N + (M - 1));
   for (int b = 0; b < M - 1; ++b) { pl.ci.push_back(levels); levels += L->N[b] + 1; sumN += L->N[b]; }

@@ -28,7 +28,8 @@ def slice_line(line: abi.HostLine, lo: int, hi: int) -> abi.HostLine:
                         portion=line.portion, w=line.w, warm_up=line.warm_up, run_to=line.run_to,
                         run_to_job=line.run_to_job, jm2dm=line.jm2dm, log=line.log, up_down=line.up_down,
                         max_lines=line.max_lines, lam_inst=cut(line.lam_inst), mu_inst=cut(line.mu_inst),
-                        W_inst=cut(line.W_inst), N_inst=cut(line.N_inst), w_inst=cut(line.w_inst))
+                        W_inst=cut(line.W_inst), N_inst=cut(line.N_inst), w_inst=cut(line.w_inst),
+                        group_rank=line.group_rank)
 
 
 def all_reduce_sum(vec: np.ndarray, group=None, device=None) -> np.ndarray:

@@ -192,6 +192,10 @@ class MultiHandle:
 
     def __init__(self, devices=None, event_hash: bool = False, reduce: int = abi.REDUCE_PEER):
         self._lib = abi.load_library()
+        if reduce == abi.REDUCE_NCCL:
+            # the library binds whatever libnccl.so.2 the process has mapped; in a Python host that is torch's
+            # bundled copy, which must be the first one loaded (a second libnccl under the same soname breaks torch)
+            import torch  # noqa: F401
         devs = None if devices is None else np.ascontiguousarray(devices, np.int32)
         cfg = abi.MultiConfig(0 if devs is None else len(devs), abi.ptr(devs, C.c_int32),
                               abi.CFG_EVENT_HASH if event_hash else 0, int(reduce))

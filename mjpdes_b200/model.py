@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-from . import abi, edn
+from . import abi, cljhash, edn
 from .philox import uniform53
 
 DEFAULTS = {":jobs-move-to-down-machines?": False, ":time-format": "~10,4f"}      # core.clj:32-34
@@ -213,7 +213,9 @@ def preprocess_model(model: dict, n_inst: int | None = None, seed: int = DEFAULT
     n = int(n_inst if n_inst is not None else (model.get(":number-of-simulations") or 1))
     line, topo = model[":line"], model[":topology"]
     machines, buffers = topo[0::2], topo[1::2]
-    jobtypes = list(model[":jobmix"].keys())             # iteration order of the :jobmix map (core.clj:332)
+    # iteration order of the :jobmix map, which new-job walks (core.clj:332): insertion order up to 8 job types,
+    # Clojure hash-map order of the job-type keywords from the 9th on
+    jobtypes = cljhash.map_order(list(model[":jobmix"].keys()))
     M, K = len(machines), len(jobtypes)
     ids = np.arange(first_instance_id, first_instance_id + n, dtype=np.uint64)
 
@@ -268,7 +270,9 @@ def preprocess_model(model: dict, n_inst: int | None = None, seed: int = DEFAULT
         run_to_job=int(params[":run-to-job"]) if params.get(":run-to-job") is not None else -1,
         jm2dm=bool(model.get(":jm2dm", DEFAULTS[":jobs-move-to-down-machines?"])),
         log=bool(rep.get(":log?", False)), up_down=bool(rep.get(":up&down?", False)),
-        max_lines=rep.get(":max-lines", 0), W_inst=W_inst, w_inst=w_inst)
+        max_lines=rep.get(":max-lines", 0), W_inst=W_inst, w_inst=w_inst,
+        # (group-by :m ...) in clean-log-buf iterates in hash-map order of these names once > 8 machines log in a tick
+        group_rank=cljhash.hash_rank(machines))
     return CompiledLine(model, host, machines, buffers, jobtypes, n, seed, first_instance_id)
 
 
@@ -298,24 +302,39 @@ def calc_basics(cl: CompiledLine, stats: abi.HostStats, inst: int) -> dict:
     }
 
 
-def calc_bneck(res: dict, machines: list) -> dict:
-    """core.clj:636-661.  bl(i)/st(i) are indexed by position in the line (the reference indexes
-    ``(vals (:blocked res))``, which coincides for M <= 8 and is keyword-hash order above)."""
-    bl = [res[":blocked"][m] for m in machines]
-    st = [res[":starved"][m] for m in machines]
+def calc_bneck(res: dict, machines: list, faithful: bool = True) -> dict:
+    """core.clj:636-661.  The reference reads bl(i) / st(i) as ``(nth (vals (:blocked res)) (dec i))``: the i-th
+    VALUE of a map built by ``into {}`` over the machines (core.clj:628-629).  Up to 8 machines that map iterates in
+    line order and bl(i) is machine i's figure; from 9 machines on it is a hash map and bl(i) is the figure of the
+    i-th machine NAME in hash order, so the reference's answer no longer follows the line.  The
+    severity map (``zipmap``, core.clj:650) is walked in the same order to pick the first maximum.
+    ``faithful=True`` reproduces exactly that (:bottleneck-machine is what the reference prints); for M > 8 the
+    rule as intended -- indexed by position in the line -- is reported beside it as
+    ``:bottleneck-machine-by-position``."""
     M = len(machines)
-    candidates = [i for i in range(M - 1) if bl[i] < st[i + 1]]
-    if len(candidates) == 1:
-        return {**res, ":bottleneck-machine": machines[candidates[0]]}
-    sev = []
-    for i in range(M):
-        if i == 0:
-            sev.append(abs(bl[0] - st[1]))
-        elif i == M - 1:
-            sev.append(abs(bl[M - 2] - st[M - 1]))
-        else:
-            sev.append(abs(bl[i - 1] - st[i]) + abs(bl[i] - st[i + 1]))
-    return {**res, ":bottleneck-machine": machines[sev.index(max(sev))]}
+
+    def rule(order):
+        bl = [res[":blocked"][m] for m in order]
+        st = [res[":starved"][m] for m in order]
+        candidates = [i for i in range(M - 1) if bl[i] < st[i + 1]]
+        if len(candidates) == 1:
+            return machines[candidates[0]]
+        sev = {}
+        for i, m in enumerate(machines):
+            if i == 0:
+                sev[m] = abs(bl[0] - st[1])
+            elif i == M - 1:
+                sev[m] = abs(bl[M - 2] - st[M - 1])
+            else:
+                sev[m] = abs(bl[i - 1] - st[i]) + abs(bl[i] - st[i + 1])
+        top = max(sev.values())
+        return next(m for m in order if sev[m] == top)             # first maximum in the severity map's iteration order
+
+    by_position = rule(machines)
+    if M <= 8 or not faithful:
+        return {**res, ":bottleneck-machine": by_position}
+    return {**res, ":bottleneck-machine": rule(cljhash.map_order(machines)),
+            ":bottleneck-machine-by-position": by_position}
 
 
 def calc_residence_time(res: dict, cl: CompiledLine, inst: int = 0) -> dict:

@@ -33,7 +33,8 @@ def build(force: bool = False) -> str:
 class Extra(C.Structure):
     _fields_ = [("act_counts", C.POINTER(C.c_uint64)), ("iterations", C.POINTER(C.c_uint64)),
                 ("ticks", C.POINTER(C.c_uint64)), ("max_tick_msgs", C.POINTER(C.c_uint32)),
-                ("max_lookahead", C.POINTER(C.c_uint32))]
+                ("max_lookahead", C.POINTER(C.c_uint32)), ("wide_ticks", C.POINTER(C.c_uint64)),
+                ("wide_ticks_reordered", C.POINTER(C.c_uint64))]
 
 
 class Basics(C.Structure):
@@ -65,6 +66,10 @@ def lib() -> C.CDLL:
         l.mjpo_calc_bneck.argtypes = [C.c_int32, pd, pd]
         l.mjpo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         l.mjpo_philox4x32_10.restype = None
+        l.mjpo_clj_keyword_hash.argtypes = [C.c_char_p]
+        l.mjpo_clj_keyword_hash.restype = C.c_uint32
+        l.mjpo_clj_trie_key.argtypes = [C.c_uint32]
+        l.mjpo_clj_trie_key.restype = C.c_uint64
         for f in (l.mjpo_log, l.mjpo_exp):
             f.argtypes = [C.c_double]
             f.restype = C.c_double
@@ -91,10 +96,12 @@ def run(line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int 
     hlog = abi.HostLog(log_capacity) if log_capacity else None
     ex = dict(act_counts=np.zeros((10, n), np.uint64), iterations=np.zeros(n, np.uint64),
               ticks=np.zeros(n, np.uint64), max_tick_msgs=np.zeros(n, np.uint32),
-              max_lookahead=np.zeros(n, np.uint32))
+              max_lookahead=np.zeros(n, np.uint32), wide_ticks=np.zeros(n, np.uint64),
+              wide_ticks_reordered=np.zeros(n, np.uint64))
     e = Extra(abi.ptr(ex["act_counts"], C.c_uint64), abi.ptr(ex["iterations"], C.c_uint64),
               abi.ptr(ex["ticks"], C.c_uint64), abi.ptr(ex["max_tick_msgs"], C.c_uint32),
-              abi.ptr(ex["max_lookahead"], C.c_uint32))
+              abi.ptr(ex["max_lookahead"], C.c_uint32), abi.ptr(ex["wide_ticks"], C.c_uint64),
+              abi.ptr(ex["wide_ticks_reordered"], C.c_uint64))
     s = stats.struct()
     ts = tapes.struct() if tapes is not None else None
     l.mjpo_set_tapes(C.byref(ts) if ts is not None else None)

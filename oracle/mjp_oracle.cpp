@@ -11,10 +11,12 @@
  *
  * Parity: pinned on the reference tests' deterministic goldens, unpinned at the
  * random-draw level (see mjp_oracle.h).  Known, documented deviations:
- *   D1  util/log.clj:44 `group-by :m` is insertion-ordered only up to 8 keys
- *       (array-map); a tick in which MORE than 8 machines log is regrouped in
- *       JVM keyword-hash order by the reference and in first-appearance order
- *       here.  Never reached for M <= 8.
+ *   D1  (closed in round 2) util/log.clj:44 `group-by :m` is insertion-ordered only up to
+ *       8 keys (array-map); a tick in which MORE than 8 machines log is regrouped in
+ *       Clojure hash-map order of the machine keywords.  That order is restated below
+ *       (clj_keyword_hash / clj_trie_key, from the published Clojure 1.9 sources: no JVM
+ *       here to execute them; (hash :a) = -2123407586 is the pinned known value).
+ *       Machine names come from the descriptor's group_rank, default :m1 .. :mM.
  *   D2  a micro-step whose minimum candidate time is ##Inf ends the instance
  *       with MJP_INST_NO_RUNABLES (the reference would set :clock ##Inf, fire
  *       every such action and report :normal-end).  Not reachable on a serial line.
@@ -22,11 +24,14 @@
  */
 #include "mjp_oracle.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <string>
+#include <utility>
 #include <thread>
 #include <vector>
 
@@ -37,6 +42,41 @@ const double kNaN = std::numeric_limits<double>::quiet_NaN();
 
 inline uint64_t d2b(double x) { uint64_t b; std::memcpy(&b, &x, 8); return b; }
 inline double b2d(uint64_t b) { double x; std::memcpy(&x, &b, 8); return x; }
+
+/* ------------------------------------------------------------------------ */
+/* Clojure map iteration order (clojure 1.9.0, project.clj:11).              */
+/* clojure.lang.Murmur3.hashUnencodedChars / Util.hashCombine / Symbol.hasheq */
+/* / Keyword.hasheq; PersistentHashMap iterates by 5-bit hash chunks, lowest  */
+/* first.  ASCII names only.                                                  */
+/* ------------------------------------------------------------------------ */
+inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+uint32_t clj_murmur3_chars(const char *name, size_t n) {
+  uint32_t h1 = 0;
+  for (size_t i = 1; i < n; i += 2) {
+    uint32_t k1 = (uint32_t)(unsigned char)name[i - 1] | ((uint32_t)(unsigned char)name[i] << 16);
+    k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u;             /* mixK1 */
+    h1 ^= k1; h1 = rotl32(h1, 13); h1 = h1 * 5u + 0xe6546b64u;             /* mixH1 */
+  }
+  if (n & 1) {
+    uint32_t k1 = (uint32_t)(unsigned char)name[n - 1];
+    k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u;
+    h1 ^= k1;
+  }
+  h1 ^= (uint32_t)(2 * n);                                                 /* fmix(h1, 2 * length) */
+  h1 ^= h1 >> 16; h1 *= 0x85ebca6bu; h1 ^= h1 >> 13; h1 *= 0xc2b2ae35u; h1 ^= h1 >> 16;
+  return h1;
+}
+uint32_t clj_keyword_hash(const char *name, size_t n) {                    /* keyword without namespace */
+  uint32_t seed = clj_murmur3_chars(name, n);
+  /* Util.hashCombine(seed, Util.hash(null) = 0): seed ^= hash + 0x9e3779b9 + (seed << 6) + (seed >> 2) */
+  uint32_t sym = seed ^ (0u + 0x9e3779b9u + (seed << 6) + (uint32_t)((int32_t)seed >> 2));
+  return sym + 0x9e3779b9u;                                                /* Keyword.hasheq */
+}
+uint64_t clj_trie_key(uint32_t h) {
+  uint64_t k = 0;
+  for (int sft = 0; sft < 35; sft += 5) k = (k << 5) | ((h >> sft) & 31u);
+  return k;
+}
 
 /* ------------------------------------------------------------------------ */
 /* Substream arithmetic (the contract in include/mjpdes_b200.h, "random      */
@@ -279,6 +319,9 @@ struct Sim {
   uint64_t n_events = 0, hash = 0xcbf29ce484222325ull, iterations = 0, ticks = 0;
   uint64_t act_counts[10] = {0};
   uint32_t max_tick_msgs = 0, max_lookahead = 0;
+  uint64_t wide_ticks = 0;            /* pushed post-warm-up ticks in which more than 8 machines logged */
+  uint64_t wide_ticks_reordered = 0;  /* ... whose cleaned batch differs from the first-appearance grouping */
+  std::vector<int> group_rank;        /* hash-map rank of machine i's name (log:44 beyond 8 groups) */
   /* SCADA sink */
   std::vector<mjp_log_record> *sink = nullptr;
   uint32_t inst_index = 0;
@@ -484,14 +527,17 @@ struct Sim {
     if (m.act == MJP_ACT_ST || m.act == MJP_ACT_US) return 1;   /* :st-us */
     return 2;                                                   /* :other */
   }
-  static void clean_log_buf(const std::vector<Msg> &acts, std::vector<Msg> &out) {
+  /* by_hash: order the machine groups as a PersistentHashMap of the machine keywords iterates */
+  void clean_log_buf(const std::vector<Msg> &acts, std::vector<Msg> &out, bool by_hash) const {
     out.clear();
-    std::vector<int> m_order;                                   /* (group-by :m), first-appearance order (D1) */
+    std::vector<int> m_order;                                   /* (group-by :m): first appearance ... */
     for (const Msg &a : acts) {
       bool seen = false;
       for (int m : m_order) if (m == a.m) { seen = true; break; }
       if (!seen) m_order.push_back(a.m);
     }
+    if (by_hash)                                                /* ... or, from the 9th key on, hash-map order */
+      std::sort(m_order.begin(), m_order.end(), [&](int a, int b) { return group_rank[a] < group_rank[b]; });
     for (int m : m_order) {
       int c_order[3], nc = 0;
       std::vector<Msg> grp[3];
@@ -507,6 +553,11 @@ struct Sim {
         for (const Msg &a : grp[c]) out.push_back(a);
       }
     }
+  }
+  static int distinct_machines(const std::vector<Msg> &acts) {
+    uint64_t seen = 0;
+    for (const Msg &a : acts) seen |= 1ull << a.m;
+    return __builtin_popcountll(seen);
   }
 
   /* ---- add-compute-log!, log:71-86 with buf+ ... end-job log:159-217 ---- */
@@ -556,7 +607,17 @@ struct Sim {
     if (max_time > min_time) {                                  /* log:98 */
       std::vector<Msg> now, later, clean;
       for (const Msg &m : log_buf) (m.clk == min_time ? now : later).push_back(m);
-      clean_log_buf(now, clean);                                /* log:100-102 */
+      const bool by_hash = distinct_machines(now) > 8;          /* array-map -> hash-map promotion (D1) */
+      clean_log_buf(now, clean, by_hash);                       /* log:100-102 */
+      if (by_hash && min_time >= warm_up) {
+        std::vector<Msg> first_app;
+        clean_log_buf(now, first_app, false);
+        wide_ticks++;
+        bool same = first_app.size() == clean.size();
+        for (size_t q = 0; same && q < clean.size(); ++q)
+          same = clean[q].m == first_app[q].m && clean[q].act == first_app[q].act;
+        if (!same) wide_ticks_reordered++;
+      }
       if (min_time >= warm_up) for (const Msg &m : clean) add_compute_log(m);   /* log:104-105 */
       bool print_now = log_on && !clean.empty() && max_lines > line_cnt && min_time >= warm_up; /* log:220-226 */
       if (print_now) print_lines(clean);
@@ -612,6 +673,18 @@ bool valid_desc(const mjp_line_desc *L, uint64_t n_inst) {
   return true;
 }
 
+std::vector<int> default_group_rank(int M) {
+  std::vector<std::pair<uint64_t, int>> keyed;
+  for (int i = 0; i < M; ++i) {
+    std::string nm = "m" + std::to_string(i + 1);
+    keyed.push_back({clj_trie_key(clj_keyword_hash(nm.data(), nm.size())), i});
+  }
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<int> rank(M);
+  for (int pos = 0; pos < M; ++pos) rank[keyed[pos].second] = pos;
+  return rank;
+}
+
 /* preprocess-model core:578-615 restricted to what the loop reads */
 const mjp_draw_tapes *g_tapes = nullptr;      /* set by mjpo_set_tapes for MJP_RNG_TAPE runs */
 
@@ -627,6 +700,9 @@ void build_sim(Sim &s, const mjp_line_desc *L, uint64_t n_inst, uint64_t g, cons
   if (rng->mode == MJP_RNG_TAPE && g_tapes) {
     s.tape_jt = g_tapes->jobtype + (size_t)g * g_tapes->len_jobtype; s.len_jt = g_tapes->len_jobtype;
   }
+  /* hash-map rank of the machine keywords: given, or that of the names :m1 .. :mM the reference's models use */
+  if (L->group_rank) s.group_rank.assign(L->group_rank, L->group_rank + s.M);
+  else s.group_rank = default_group_rank(s.M);
   s.clock = 0.0; s.warm_up = L->warm_up; s.run_to = L->run_to; s.run_to_job = L->run_to_job;
   s.jm2dm = L->jm2dm; s.log_on = L->log; s.up_down = L->up_down; s.max_lines = L->max_lines;
   for (int i = 0; i < s.M; ++i) {
@@ -736,6 +812,8 @@ int mjpo_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng,
         if (extra->iterations) extra->iterations[g] = s.iterations;
         if (extra->ticks) extra->ticks[g] = s.ticks;
         if (extra->max_tick_msgs) extra->max_tick_msgs[g] = s.max_tick_msgs;
+        if (extra->wide_ticks) extra->wide_ticks[g] = s.wide_ticks;
+        if (extra->wide_ticks_reordered) extra->wide_ticks_reordered[g] = s.wide_ticks_reordered;
         if (extra->max_lookahead) extra->max_lookahead[g] = s.max_lookahead;
       }
     }
@@ -803,6 +881,7 @@ int mjpo_updown_events(double lambda, double mu, const mjp_rng_spec *rng, uint64
 int mjpo_log_script(int32_t M, const int32_t *N, double warm_up, uint8_t up_down, const uint8_t *ops,
                     const mjp_log_record *msgs, int32_t n_ops, mjp_stats_out *stats, mjp_log_out *log) {
   Sim s; s.M = M; s.warm_up = warm_up; s.up_down = up_down;
+  s.group_rank = default_group_rank(M);
   s.N.assign(N, N + (M > 1 ? M - 1 : 0));
   s.log_on = (log != nullptr); s.max_lines = UINT64_MAX;
   std::vector<mjp_log_record> sink; if (log) s.sink = &sink;
@@ -863,6 +942,8 @@ int mjpo_calc_bneck(int32_t M, const double *bl, const double *st) {
   return best;
 }
 
+uint32_t mjpo_clj_keyword_hash(const char *name) { return clj_keyword_hash(name, std::strlen(name)); }
+uint64_t mjpo_clj_trie_key(uint32_t hash) { return clj_trie_key(hash); }
 void mjpo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
 double mjpo_log(double x) { return det_log(x); }
 double mjpo_exp(double x) { return det_exp(x); }

@@ -33,7 +33,14 @@ typedef struct mjpo_extra {
   uint64_t *ticks;          /* [n] distinct clock values                      */
   uint32_t *max_tick_msgs;  /* [n] largest same-clock message batch           */
   uint32_t *max_lookahead;  /* [n] deepest end-time look-ahead (events past :future) */
+  uint64_t *wide_ticks;     /* [n] post-warm-up ticks in which more than 8 machines logged (hash-map regrouping) */
+  uint64_t *wide_ticks_reordered; /* [n] ... of which the cleaned batch differs from first-appearance grouping */
 } mjpo_extra;
+
+/* Position of `name` (a keyword without colon or namespace, e.g. "m7") in Clojure hash-map iteration order is
+ * decided by this key: PersistentHashMap walks its trie by ascending 5-bit chunks of the key's hasheq.        */
+uint32_t mjpo_clj_keyword_hash(const char *name);
+uint64_t mjpo_clj_trie_key(uint32_t hash);
 
 /* main-loop-loop (core.clj:729-744) for instances [0, n_inst) on n_threads
  * host threads.  Same descriptor / rng / output structs as mjp_run().       */

@@ -23,6 +23,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   kp.lam = dc + pl.off_lam(); kp.mu = dc + pl.off_mu(); kp.W = dc + pl.off_W(); kp.w = dc + pl.off_w();
   kp.dur = dc + pl.off_dur(); kp.thr = dc + pl.off_thr();
   kp.N = pl.ci.data(); kp.lvl = pl.ci.data() + (M - 1);
+  kp.by_rank = pl.by_rank.data();
   kp.lam_i = L->lambda_inst; kp.mu_i = L->mu_inst; kp.W_i = L->W_inst; kp.w_i = L->w_inst; kp.N_i = L->N_inst;
   const bool want_log_early = log && L->log;
   const bool sweep = n_slices > 0;     // template slot 5 is SLICE; override planes are a run-time check
