@@ -24,7 +24,8 @@ Printed keys beyond the base contract:
   configs   time-boxed runs of the other named shapes, each with its own roofline:
             C3  the 10-machine sweep, STRONG scaling: the 1M grid points divided over the N GPUs
             C4  20 machines, mixed BAS/BBS, 8 job types, 10 000 instances per GPU: statistics only (full
-                horizon) and with SCADA capture over the window 2000..3000 (record bytes/s over the window)
+                horizon; also with 75 776 instances, which fill the GPU) and with SCADA capture over the window
+                2000..3000 (record bytes/s over the window)
             C5  50 machines, 16 job types, 10M/8 = 1.25M resident instances per GPU, each advanced by a
                 sim-time quantum through mjp_launch_slice with its state parked in HBM (weak scaling)
   cpu_baseline  the CPU oracle (a C++ restatement, NOT the JVM reference: no JVM exists in this
@@ -259,6 +260,14 @@ def bench_configs(args, cl: Cluster, h, peak_gwis: float, hbm_gbs: float) -> dic
     finish("C4_mixed20_stats", ms, float(st.n_events.sum()),
            {"scaling": "weak", "instances_per_gpu": n4, "all_normal_end": bool(np.all(st.status == abi.INST_NORMAL_END)),
             "shape": "M=20 mixed BAS/BBS K=8, statistics only, warm-up 2000, run-to 20000"})
+    # the same line with enough instances to fill the GPU (10 000 thread-per-instance lanes are 68 per SM)
+    n4s = args.c4_saturated
+    h.upload(wl.mixed20_line(log=False), n4s)
+    ms = timed_launch(first_instance_id=10 ** 7 + rank * n4s)
+    st = h.download_fields(("n_events", "status"))
+    finish("C4_mixed20_stats_saturated", ms, float(st.n_events.sum()),
+           {"scaling": "weak", "instances_per_gpu": n4s, "all_normal_end": bool(np.all(st.status == abi.INST_NORMAL_END)),
+            "shape": "M=20 mixed BAS/BBS K=8, statistics only, warm-up 2000, run-to 20000; instance count that fills one GPU"})
     # SCADA capture over the window 2000..3000 (the full horizon would be 173 GB of records per 10 000 instances):
     # window time = (run to 3000 with capture) - (the capture-free run to 2000 of the same instances)
     h.upload(wl.mixed20_line(warm_up=2000.0, run_to=2000.001, log=False, up_down=True), n4)
@@ -320,6 +329,7 @@ def main():
     ap.add_argument("--skip-configs", action="store_true", help="headline only (no C3/C4/C5 runs)")
     ap.add_argument("--c3-points", type=int, default=1_000_000, help="grid points of the C3 sweep (whole job)")
     ap.add_argument("--c4-instances", type=int, default=10_000, help="C4 instances per GPU")
+    ap.add_argument("--c4-saturated", type=int, default=75_776, help="C4 instances per GPU of the saturated run")
     ap.add_argument("--c5-instances", type=int, default=1_250_000, help="C5 resident instances per GPU")
     ap.add_argument("--c5-quantum0", type=float, default=20.0)
     ap.add_argument("--c5-quantum", type=float, default=60.0, help="sim time of the timed C5 slice")

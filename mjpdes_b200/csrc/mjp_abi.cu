@@ -45,6 +45,8 @@ struct mjp_handle {
   int flags = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  size_t l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 set-aside and access-policy window limits
+  bool l2_persist_used = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -52,7 +54,7 @@ struct mjp_handle {
   bool uploaded = false, launched = false, sweep = false;
   mjp::KParams kp{};
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage, d_dur;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -204,6 +206,8 @@ int mjp_create(const mjp_config *cfg, mjp_handle **out) {
   }
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+  h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   *out = h;
   return MJP_OK;
 }
@@ -213,7 +217,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage})
+                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage, &h->d_dur})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -279,6 +283,19 @@ static int upload_impl(mjp_handle *h, const mjp_line_desc *L, uint64_t n_inst, u
     kp.w_i = (const double *)put(L->w_inst, sizeof(double), (size_t)K * M, pKM);
     kp.N_i = (const int32_t *)put(L->N_inst, sizeof(int32_t), (size_t)(M - 1), pN);
     CK(cudaGetLastError());
+  }
+  kp.dur_i = nullptr;
+  if (kp.W_i || kp.w_i) {
+    // sweeps over W / w: divide w by W once per (job type, machine, instance) instead of at every job start;
+    // skipped (the loop then divides) when the plane would be unreasonably large
+    const size_t bytes = (size_t)K * M * n_inst * sizeof(double);
+    if (bytes <= ((size_t)4 << 30)) {
+      CK(h->d_dur.reserve(bytes));
+      const int blocks = (int)std::min<size_t>(((size_t)K * M * n_inst + 255) / 256, (size_t)h->sm_count * 16);
+      mjp::mjp_dur_plane<<<blocks, 256, 0, h->stream>>>(kp, h->d_dur.as<double>());
+      CK(cudaGetLastError());
+      kp.dur_i = h->d_dur.as<double>();
+    }
   }
 
   // ---- outputs: [blocked | starved | occ] are accumulated into and must be zeroed per launch ----
@@ -442,7 +459,30 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     const bool slice = resume || until < std::numeric_limits<double>::infinity();
     mjp::KParams kl = kp;                         // tapes are read by MJP_RNG_TAPE launches only
     if (rng->mode != MJP_RNG_TAPE) kl.tape_jt = kl.tape_u = kl.tape_e = nullptr;
+    // COLD layouts: the cold per-instance state is re-read all through the run while statistics, job-entry times
+    // and SCADA records stream past it; pin it in the L2 (persisting access-policy window on the handle's stream)
+    static const char *persist_env = std::getenv("MJP_L2_PERSIST");       // A/B measurements: 0 = off
+    const bool persist = cold && h->l2_persist_max && h->l2_window_max && !(persist_env && persist_env[0] == '0');
+    if (persist) {
+      const size_t cold_bytes = std::min(h->d_cold.cap, h->l2_window_max);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max);
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.base_ptr = h->d_cold.ptr;
+      av.accessPolicyWindow.num_bytes = cold_bytes;
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist_max / (double)cold_bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+      cudaGetLastError();                                                  // best effort: a refusal is not an error
+    }
     cudaError_t e = launch_line_kernel(replay, hash, slice, h->want_log, cold, kl, blocks, threads, h->smem_bytes, h->stream);
+    if (persist) {
+      h->l2_persist_used = true;
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+      cudaGetLastError();
+    }
     CK(e);
     launches++;
   }
@@ -467,6 +507,7 @@ int mjp_sync(mjp_handle *h) {
   if (!h) return MJP_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->l2_persist_used) { cudaCtxResetPersistingL2Cache(); h->l2_persist_used = false; }   // hand the set-aside L2 back
   if (h->launched) CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   return MJP_OK;
 }

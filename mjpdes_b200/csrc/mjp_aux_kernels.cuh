@@ -5,6 +5,19 @@
 
 namespace mjp {
 
+// ---- job-requires (utils.clj:95-101) for sweeps: w/W of every (job type, machine, instance), divided once --------
+// The same correctly rounded division the loop would do at every job start (dur_of in mjp_line_kernel.cuh).
+__global__ void mjp_dur_plane(const KParams p, double *dur) {
+  const size_t n = p.n_inst, total = (size_t)p.K * p.M * n;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = q / n, g = q - row * n;
+    const int i = (int)(row % p.M);
+    const double wv = p.w_i ? p.w_i[q] : p.w[row];
+    const double Wv = p.W_i ? p.W_i[(size_t)i * n + g] : p.W[i];
+    dur[q] = __ddiv_rn(wv, Wv);
+  }
+}
+
 // ---- aggregate: calc-basics (core.clj:617-634) per instance, then sum(x), sum(x^2) -------------
 // One block-wide tree per metric; partials[block][metric] are summed in a fixed
 // order by mjp_aggregate_final, so the result does not depend on scheduling.

@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define EJENT      sf[(hb + 1) * nt]            /* :ent of this tick's :ej            */
 #define TMINUD     sf[(hb + 2) * nt]            /* earliest pending up/down time (cache) */
 #define ENDS_S(i)  sf[(hb + 3 + (i)) * nt]      /* :status :ends, or remaining work (MT == 0 only) */
+#define GMINE(gr)     sf[(hb + 3 + M + (gr)) * nt]      /* MT == 0: min :ends over the tracked machines of group gr   */
+#define GMINU(gr)     sf[(hb + 3 + M + G + (gr)) * nt]  /* MT == 0: min pending up/down time over group gr            */
 #define FUT_N(i)   cup[(i) * cs]                 /* :future index                      */
 #define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
 #define CNT(b)     su[(hu + (b)) * nt]          /* bits 0-7 (count :holding) of buffer b; bits 8-18 this tick's
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   auto mu_of = [&](int i) -> double { return (p.mu_i != nullptr) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
   auto cap_of = [&](int b) -> int { return (flags & F_CAPPL) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
   auto dur_of = [&](int k, int i) -> double {
+    if (p.dur_i != nullptr) return p.dur_i[(size_t)(k * M + i) * n_inst + g];   // job-requires, divided once at upload
     if (flags & F_DURPL) {
       const double wv = p.w_i ? p.w_i[(size_t)(k * M + i) * n_inst + g] : p.w[k * M + i];
       const double Wv = p.W_i ? p.W_i[(size_t)i * n_inst + g] : p.W[i];
@@ -377,7 +380,20 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   }
   for (int b = 0; fresh_start && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
   for (int b = 0; fresh_start && b < M - 1; ++b) CNT(b) = (uint32_t)cap_of(b) << 24;   // :N <= 254 (mjp_upload)
-  // min over the machines' pending up/down times and who attains it: changes only when one fires
+  // Wide lines (MT == 0): the two minima a micro-step needs -- the earliest strictly-future :ends among the
+  // machines that own an :ends candidate, and the earliest pending up/down time -- are kept per GROUP of 8
+  // machines (GMINE / GMINU) and maintained incrementally, so that no pass over all M machines is left on the
+  // per-micro-step path: a group is re-read only when its minimum is consumed or a member leaves it.
+  const int G = (M + 7) >> 3;
+  auto grp_bits = [&](MaskT m, int gr) -> uint32_t { return (uint32_t)(m >> (8 * gr)) & 0xFFu; };
+  // min of :ends over the machines `members` (a byte: bit j = machine 8 gr + j) of group gr
+  auto group_min_ends = [&](int gr, uint32_t members) -> double {
+    double acc = INF;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if ((members >> j) & 1u) { const double e = ENDS_S(8 * gr + j); acc = e < acc ? e : acc; }
+    return acc;
+  };
+  // min over the machines' pending up/down times and who attains it: changes only when one fires (MT > 0)
   MaskT m_udc = 0;
   auto rescan_fut = [&]() {
     double t0 = INF;
@@ -389,11 +405,26 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
     TMINUD = t0;
   };
-  if (fresh_start) rescan_fut();
+  if (fresh_start) {
+    if (MT > 0) rescan_fut();
+    else {
+      double t0 = INF;
+      for (int gr = 0; gr < G; ++gr) {
+        double acc = INF;
+        for (int i = 8 * gr; i < 8 * gr + 8 && i < M; ++i) { const double t = FUT_T(i); acc = t < acc ? t : acc; }
+        GMINU(gr) = acc; GMINE(gr) = INF;
+        t0 = acc < t0 ? acc : t0;
+      }
+      TMINUD = t0;
+    }
+  }
 
   // ---- model state in registers ---------------------------------------------
   double clock = 0.0;
   MaskT occ = 0, B = 0, S = 0, full = 0, pend = 0, dup = 0, fired = 0;
+  // MT == 0: `late` (machines whose job is over: occupied, not pending, clock >= :ends) is carried from micro-step
+  // to micro-step, and `tracked` is the set of machines whose :ends is accounted for in GMINE (all strictly future)
+  MaskT late = 0, tracked = 0;
   MaskT need = ALL;                             // machines whose NXT_T has not been generated yet
   MaskT empty = ALL & ~(MaskT)1;               // feed-buffer-empty? (nil for the entry machine, utils.clj:85)
   const MaskT upj = p.jm2dm ? ALL : (MaskT)0;  // :jm2dm, core.clj:490,495
@@ -617,6 +648,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     double v;
     if (end_time_begin((up & bit) != 0, FUT_T(i), clock, dur_of(type, i), v)) pend |= bit; else pend &= ~bit;
     set_end(i, v);
+    if (MT == 0) late &= ~bit;                              // a new job: not over, not tracked yet
   };
 
   // ---- time slicing: the complete per-instance state, parked in HBM as [word][instance] ----
@@ -627,7 +659,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define MJP_PARK_LIST(D, MK, U, Q)                                                                          \
   D(clock)                                                                                                  \
   MK(up) MK(occ) MK(B) MK(S) MK(full) MK(empty) MK(pend) MK(dup) MK(fired) MK(need)                         \
-  MK(seen) MK(lead) MK(touched) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc)                \
+  MK(seen) MK(lead) MK(touched) MK(pB) MK(twoB) MK(pS) MK(twoS) MK(m_udc) MK(late) MK(tracked) \
   U(curjob) U(n_ev) U(flags) U(tq)   /* (flags is parked before the :status code is put into it) */
   // state that exists only in some variants (parking it unconditionally would keep it alive everywhere)
 #define MJP_PARK_LOG(D, U) D(aj_ends) U(line_cnt) U(n_staged)
@@ -725,20 +757,48 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     const MaskT cand = c_tb | c_bla;
     const double tmin_ud = TMINUD;
     double tmin = tmin_ud;
-    MaskT late = 0;
+    double te = INF;                                         // MT == 0: earliest tracked :ends
+    uint32_t ge_arg = 0;                                     // MT == 0: groups that attain it
     if (MT > 0) {                                            // :ends in registers: the late mask first ...
+      late = 0;
 #pragma unroll
       for (int i = 0; i < MT; ++i) if (clock >= r_end[i]) late |= MJP_BIT(i);
-    } else {                                                 // :ends in shared memory: one pass, one load each
-      for (int i = 0; i < M; ++i) {
-        const double e = ENDS_S(i);
-        const bool over = clock >= e;
-        if (over) late |= MJP_BIT(i);
-        const double ef = ((cand & MJP_BIT(i)) && !over) ? e : INF;
-        tmin = ef < tmin ? ef : tmin;
+      late &= occ & ~pend;
+    } else {
+      // (a) a job that is over on a machine WITHOUT an :ends candidate (a :BBS machine working into a full buffer)
+      // passes unnoticed; new-starved? (finished?, utils.clj:68-74) is the one guard that can see it
+      for (MaskT q = live ? (occ & ~pend & ~late & ~cand & empty & ~S) : (MaskT)0; __any_sync(am, q != 0);) if (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        if (clock >= ENDS_S(i)) late |= MJP_BIT(i);
       }
+      // (b) machines that joined or left the candidates since the last micro-step (a job started or was resumed;
+      // a buffer filled up or drained behind a :BBS machine)
+      const MaskT fut0 = cand & ~late;
+      uint32_t gdirty = 0;
+      for (MaskT q = live ? (tracked & ~fut0) : (MaskT)0; __any_sync(am, q != 0);) if (q) {
+        const int gr = MO::ffs(q) >> 3;
+        q &= ~((MaskT)0xFFu << (8 * gr));
+        gdirty |= 1u << gr;                                  // a member left: the group's minimum is re-read below
+      }
+      for (MaskT q = live ? (fut0 & ~tracked) : (MaskT)0; __any_sync(am, q != 0);) if (q) {
+        const int i = MO::ffs(q); q &= q - 1;
+        const double e = ENDS_S(i);
+        if (clock >= e) late |= MJP_BIT(i);                  // already over: a "now" candidate, never tracked
+        else { const int gr = i >> 3; const double cur = GMINE(gr); GMINE(gr) = e < cur ? e : cur; }
+      }
+      if (live) tracked = cand & ~late;
+      for (uint32_t q = gdirty; __any_sync(am, q != 0);) if (q) {
+        const int gr = __ffs((int)q) - 1; q &= q - 1;
+        GMINE(gr) = group_min_ends(gr, grp_bits(tracked, gr));
+      }
+      // (c) the earliest of them: G group minima instead of M machines
+      for (int gr = 0; gr < G; ++gr) {
+        const double v = GMINE(gr);
+        if (v < te) { te = v; ge_arg = 0u; }
+        if (v == te) ge_arg |= 1u << gr;
+      }
+      tmin = te < tmin ? te : tmin;
     }
-    late &= occ & ~pend;
     const MaskT c_st = ~S & empty & (~occ | late) & ALL;       // finished? = no job or clock >= :ends   core.clj:451-460, utils.clj:68-74
     const MaskT tb_now = c_tb & late, bl_now = c_bla & late, fut = cand & ~late;
     const bool now_any = (c_aj | c_tm | c_st | c_us | c_ub | c_blb | dup | tb_now | bl_now) != 0;
@@ -762,12 +822,49 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
     const double tstar = now_any ? clock : tmin;
     MaskT m_f = 0;                                            // future :ends equal to t*
-    if (!now_any) {
+    MaskT m_ud = 0;                                           // pending up/down events at t*
+    if (MT > 0) {
+      if (!now_any) {
 #pragma unroll
-      for (int i = 0; i < (MT > 0 ? MT : M); ++i)
-        if ((fut & MJP_BIT(i)) && (MT > 0 ? r_end[i] : ENDS_S(i)) == tstar) m_f |= MJP_BIT(i);
+        for (int i = 0; i < MT; ++i) if ((fut & MJP_BIT(i)) && r_end[i] == tstar) m_f |= MJP_BIT(i);
+      }
+      m_ud = (tmin_ud == tstar) ? (m_udc & ~dup) : (MaskT)0;
+    } else {
+      // the groups whose minimum is t*: their members at t* fire (and leave the tracked set: the clock has
+      // reached their :ends), the others give the group's new minimum -- one pass does both
+      for (uint32_t q = (live && !now_any && te == tstar) ? ge_arg : 0u; __any_sync(am, q != 0);) if (q) {
+        const int gr = __ffs((int)q) - 1; q &= q - 1;
+        const uint32_t members = grp_bits(tracked, gr);
+        uint32_t hit = 0;
+        double acc = INF;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if ((members >> j) & 1u) {
+          const double e = ENDS_S(8 * gr + j);
+          if (e == tstar) hit |= 1u << j; else acc = e < acc ? e : acc;
+        }
+        GMINE(gr) = acc;
+        m_f |= (MaskT)hit << (8 * gr);
+      }
+      tracked &= ~m_f;
+      late |= m_f;                                            // (every use of the pre-advance `late` is above)
+      // same for the up/down times: members of the groups at t* that fire, new group minimum over the others
+      // (the fired machines add their next event time below)
+      uint32_t uq = 0;
+      if (live && tmin_ud == tstar) for (int gr = 0; gr < G; ++gr) if (GMINU(gr) == tstar) uq |= 1u << gr;
+      for (; __any_sync(am, uq != 0);) if (uq) {
+        const int gr = __ffs((int)uq) - 1; uq &= uq - 1;
+        const uint32_t is_dup = grp_bits(dup, gr);
+        uint32_t hit = 0;
+        double acc = INF;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (8 * gr + j < M) {
+          const double t = FUT_T(8 * gr + j);
+          if (t == tstar && !((is_dup >> j) & 1u)) hit |= 1u << j; else acc = t < acc ? t : acc;
+        }
+        GMINU(gr) = acc;
+        m_ud |= (MaskT)hit << (8 * gr);
+      }
     }
-    const MaskT m_ud = (tmin_ud == tstar) ? (m_udc & ~dup) : (MaskT)0;
     const MaskT keep = live ? ~(MaskT)0 : (MaskT)0, keep_now = (live && now_any) ? ~(MaskT)0 : (MaskT)0;
     MaskT b_aj = c_aj & keep_now;
     MaskT b_tm = c_tm & keep_now, b_st = c_st & keep_now, b_us = c_us & keep_now, b_ub = c_ub & keep_now;
@@ -850,6 +947,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
     {                                                        // bring-machine-up, then -down: core.clj:215-238
       // M <= 8: both masks are one 32-bit list (ups in bits 0-7, downs in bits 8-15)
+      const MaskT dup_before = dup;
       uint32_t q32 = MT > 0 ? ((uint32_t)(b_ud & ~up) | ((uint32_t)(b_ud & up) << 8)) : 0u;
       MaskT q_up = MT > 0 ? (MaskT)0 : (b_ud & ~up), q_dn = MT > 0 ? (MaskT)0 : (b_ud & up);
       while (__any_sync(am, MT > 0 ? q32 != 0u : (q_up | q_dn) != 0)) if (MT > 0 ? q32 != 0u : (q_up | q_dn) != 0) {
@@ -886,7 +984,15 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
             if (!end_time_resume(t_fire, t_next, get_end(i), v)) pend &= ~bit;
             set_end(i, v);
           }
-          rescan_fut();
+          if (MT > 0) rescan_fut();
+          else { const int gr = i >> 3; const double cur = GMINU(gr); GMINU(gr) = t_next < cur ? t_next : cur; }
+        }
+      }
+      if (MT == 0 && __any_sync(am, (b_ud & ~dup_before) != 0)) {
+        if (b_ud & ~dup_before) {                            // an event fired: the earliest pending up/down time anew
+          double t0 = INF;
+          for (int gr = 0; gr < G; ++gr) { const double v = GMINU(gr); t0 = v < t0 ? v : t0; }
+          TMINUD = t0;
         }
       }
     }
@@ -912,6 +1018,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         flags |= F_EJ; EJENT = ent;
       }
       occ &= ~bit;
+      if (MT == 0) late &= ~bit;
     }
     for (MaskT q = b_tm; __any_sync(am, q != 0);) if (q) {   // advance2machine core.clj:263-277
       const int i = MO::ffs(q); q &= q - 1;
@@ -986,6 +1093,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   if (HASH && p.hash) p.hash[g] = h;
 #undef FUT_T
 #undef ENDS_S
+#undef GMINE
+#undef GMINU
 #undef TMINUD
 #undef NXT_T
 #undef TICKCLK

@@ -25,6 +25,7 @@ struct KParams {
   const uint8_t *by_rank;                       // [M] machines in Clojure hash-map order of their names
   // per-instance override planes, instance-fastest (nullptr = absent)
   const double *lam_i, *mu_i, *W_i, *w_i;
+  const double *dur_i;    // [K*M][n_inst] w/W per instance, precomputed at upload when W_i or w_i is present (nullptr: divide in the loop)
   const int32_t *N_i;
   // outputs, instance-fastest (zero-initialised by the host before launch)
   int64_t *njobs; double *residence; double *blocked, *starved, *occ; double *final_clock;

@@ -67,7 +67,7 @@ inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Per-thread shared-memory slots of one kernel variant (must mirror the macros in mjp_line_kernel.cuh):
 //   cold f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1]         cold u32: FUT_N[M] STARTED[M] JT[R/4] EIDX[M] if REPLAY
-//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] unless in registers
+//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] GE[G] GU[G] unless :ends are in registers (G = ceil(M/8) groups)
 //   hot  u32: CNT[M-1]
 // SCADA capture (LOG) stages a tick's messages in a global scratch of stage_cap words per instance, not here.
 // Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX);
@@ -79,7 +79,7 @@ inline int cold_u32_slots(const KParams &kp, bool replay) {
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
   (void)log;
-  kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : M);
+  kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : M + 2 * ((M + 7) / 8));
   kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1);
   return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
 }

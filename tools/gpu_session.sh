@@ -25,6 +25,14 @@ prof() {   # name
   cat $O/${TAG}_$1_events.json; echo
   timeout 900 $NCU -f -o $O/${TAG}_$1 python tools/profile_config.py $1 > $O/${TAG}_$1_ncu.log 2>&1; echo "ncu $1 exit $?"
 }
+if has ab_persist; then
+  for c in C3_sweep10 C4_mixed20_stats_many C5_long50 C5_long50_slice C4_mixed20_scada example_scada; do
+    for v in 0 1; do
+      echo -n "persist=$v $c: "; MJP_L2_PERSIST=$v timeout 600 python tools/profile_config.py $c 2>&1 | tail -1
+    done
+  done > $O/${TAG}_ab_persist.log 2>&1
+  cat $O/${TAG}_ab_persist.log
+fi
 if has ncu_c2; then prof C2_example; fi
 if has ncu_wide; then prof C3_sweep10; prof C4_mixed20_stats_many; prof C5_long50; fi
 if has ncu_c4; then prof C4_mixed20_stats; fi
