@@ -54,7 +54,7 @@ struct mjp_handle {
   bool uploaded = false, launched = false, sweep = false;
   mjp::KParams kp{};
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage, d_dur;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage, d_dur, d_rot;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -152,10 +152,10 @@ static bool use_register_ends(const mjp::KParams &kp, bool log, int threads) {
 }
 
 static cudaError_t launch_line_kernel(bool replay, bool hash, bool slice, bool log, bool cold, const mjp::KParams &kp,
-                                      int blocks, int threads, size_t smem, cudaStream_t st) {
+                                      int blocks, int threads, size_t smem, cudaStream_t st, int *occupancy = nullptr) {
 #define MJP_GO(T, MT, COLD)                                                                          \
-  return log ? mjp::launch_flags<T, MT, COLD, true>(replay, hash, slice, kp, blocks, threads, smem, st) \
-             : mjp::launch_flags<T, MT, COLD, false>(replay, hash, slice, kp, blocks, threads, smem, st)
+  return log ? mjp::launch_flags<T, MT, COLD, true>(replay, hash, slice, kp, blocks, threads, smem, st, occupancy) \
+             : mjp::launch_flags<T, MT, COLD, false>(replay, hash, slice, kp, blocks, threads, smem, st, occupancy)
   if (cold) { if (kp.M > 32) MJP_GO(uint64_t, 0, true); MJP_GO(uint32_t, 0, true); }
   if (kp.M > 32) MJP_GO(uint64_t, 0, false);
   if (use_register_ends(kp, log, threads)) {
@@ -217,7 +217,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage, &h->d_dur})
+                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage, &h->d_dur, &h->d_rot})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -440,7 +440,7 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     const bool mt = !cold && use_register_ends(kp, h->want_log, threads);
     const size_t per_thread = mjp::plan_layout(kp, mt, replay, h->want_log, cold);
     if (cold) {
-      const size_t fb = mjp::plan_align_up((size_t)mjp::cold_f64_slots(kp) * kp.n_inst * 8, 256);
+      const size_t fb = mjp::plan_align_up((size_t)(mjp::cold_f64_slots(kp) + mjp::cold_ends_slots(kp)) * kp.n_inst * 8, 256);
       CK(h->d_cold.reserve(fb + (size_t)mjp::cold_u32_slots(kp, replay) * kp.n_inst * 4));
       kp.cold_f = h->d_cold.as<double>();
       kp.cold_u = reinterpret_cast<uint32_t *>((char *)h->d_cold.ptr + fb);
@@ -450,19 +450,44 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
       kp.stage = h->d_stage.as<unsigned long long>();
     }
     h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
-    if (resume || until < std::numeric_limits<double>::infinity()) {   // == slice
+    int blocks = (int)((kp.n_inst + threads - 1) / threads);
+    // Rotation: a complete run of a batch that needs between one and four waves of CTAs is cut into slices of
+    // sim time, and the resident CTAs pull (chunk, slice) items from a queue (mjp_line_kernel.cuh): all instances
+    // of a batch take about the same time, so otherwise the last, partly filled wave would cost a full pass.
+    kp.rot_slices = 0;
+    static const char *rot_env = std::getenv("MJP_ROTATE");               // A/B measurements: 0 = never
+    static const char *rot_slices_env = std::getenv("MJP_ROTATE_SLICES");
+    if (!resume && until == std::numeric_limits<double>::infinity() && std::isfinite(kp.run_to) &&
+        !(rot_env && rot_env[0] == '0')) {
+      int occ = 0;
+      cudaError_t oe = launch_line_kernel(replay, hash, true, h->want_log, cold, kp, 0, threads, h->smem_bytes, h->stream, &occ);
+      const long long capacity = (oe == cudaSuccess) ? (long long)occ * (long long)sms : 0;
+      if (capacity > 0 && blocks > capacity && blocks < 4 * capacity) {
+        kp.rot_slices = rot_slices_env ? std::max(2, std::atoi(rot_slices_env)) : 16;
+        kp.rot_chunks = (uint32_t)blocks;
+        kp.rot_dt = kp.run_to / (double)kp.rot_slices;
+        CK(h->d_rot.reserve(4 * ((size_t)blocks + 1)));
+        CK(cudaMemsetAsync(h->d_rot.ptr, 0, 4 * ((size_t)blocks + 1), h->stream));
+        kp.rot_queue = h->d_rot.as<uint32_t>();
+        kp.rot_flags = h->d_rot.as<uint32_t>() + 1;
+        blocks = (int)capacity;
+      }
+      cudaGetLastError();
+    }
+    const bool rotate = kp.rot_slices > 0;
+    if (rotate || resume || until < std::numeric_limits<double>::infinity()) {   // == slice
       kp.park_words = 72 + 2 * kp.nf64 + kp.nu32;     // loop-carried registers (<= 72 words) + every shared slot
       CK(h->d_park.reserve((size_t)kp.park_words * kp.n_inst * 4));
       kp.park = h->d_park.as<uint32_t>();
     }
-    const int blocks = (int)((kp.n_inst + threads - 1) / threads);
-    const bool slice = resume || until < std::numeric_limits<double>::infinity();
+    const bool slice = rotate || resume || until < std::numeric_limits<double>::infinity();
     mjp::KParams kl = kp;                         // tapes are read by MJP_RNG_TAPE launches only
     if (rng->mode != MJP_RNG_TAPE) kl.tape_jt = kl.tape_u = kl.tape_e = nullptr;
     // COLD layouts: the cold per-instance state is re-read all through the run while statistics, job-entry times
     // and SCADA records stream past it; pin it in the L2 (persisting access-policy window on the handle's stream)
-    static const char *persist_env = std::getenv("MJP_L2_PERSIST");       // A/B measurements: 0 = off
-    const bool persist = cold && h->l2_persist_max && h->l2_window_max && !(persist_env && persist_env[0] == '0');
+    static const char *persist_env = std::getenv("MJP_L2_PERSIST");       // A/B measurements: 1 = on
+    // (measured on C3 / C4 / C5 and both SCADA shapes: no gain, 0-3 % loss -- kept as an opt-in, MJP_L2_PERSIST=1)
+    const bool persist = cold && h->l2_persist_max && h->l2_window_max && persist_env && persist_env[0] == '1';
     if (persist) {
       const size_t cold_bytes = std::min(h->d_cold.cap, h->l2_window_max);
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max);

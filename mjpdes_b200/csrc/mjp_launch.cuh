@@ -11,9 +11,10 @@
 
 namespace mjp {
 
+// occupancy != nullptr: do not launch, report how many CTAs of that instantiation fit on one SM
 template <typename MaskT, int MT, bool COLD, bool LOG>
 cudaError_t launch_flags(bool replay, bool hash, bool slice, const KParams &kp, int blocks, int threads, size_t smem,
-                         cudaStream_t st);
+                         cudaStream_t st, int *occupancy);
 
 #define MJP_FAMILIES(X)                                                                                      \
   X(uint32_t, 0, false) X(uint32_t, 2, false) X(uint32_t, 3, false) X(uint32_t, 4, false) X(uint32_t, 5, false) \
@@ -22,8 +23,8 @@ cudaError_t launch_flags(bool replay, bool hash, bool slice, const KParams &kp, 
 
 #ifndef MJP_V_MASK
 #define MJP_X(T, MT, COLD)                                                                                   \
-  extern template cudaError_t launch_flags<T, MT, COLD, false>(bool, bool, bool, const KParams &, int, int, size_t, cudaStream_t); \
-  extern template cudaError_t launch_flags<T, MT, COLD, true>(bool, bool, bool, const KParams &, int, int, size_t, cudaStream_t);
+  extern template cudaError_t launch_flags<T, MT, COLD, false>(bool, bool, bool, const KParams &, int, int, size_t, cudaStream_t, int *); \
+  extern template cudaError_t launch_flags<T, MT, COLD, true>(bool, bool, bool, const KParams &, int, int, size_t, cudaStream_t, int *);
 MJP_FAMILIES(MJP_X)
 #undef MJP_X
 #endif

@@ -61,6 +61,31 @@ template <> struct MaskOps<uint64_t> {
 
 __device__ __forceinline__ void hmix(uint64_t &h, uint64_t w) { h = (h ^ w) * 0x100000001b3ull; }
 
+// release / acquire on a device-scope flag, and a short sleep while polling it (rotation, see the kernel)
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+#ifdef __CUDA_ARCH__
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void nano_sleep(unsigned ns) {
+#ifdef __CUDA_ARCH__
+  __nanosleep(ns);
+#else
+  (void)ns;
+#endif
+}
+
 // fire-and-forget add into an output plane
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 
@@ -217,7 +242,7 @@ static __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid,
 // SLICE: the launch may stop at a slice boundary and/or resume parked instances (mjp_launch_slice); kept out
 // of the plain variants because the park/unpark code keeps every state variable alive (4 % on the headline).
 template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SLICE, bool LOG, bool COLD = false>
-__global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kernel(const KParams p) {
+__global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = (MT > 0) ? MJP_FIXED_NT : (int)blockDim.x, M = (MT > 0) ? MT : p.M, K = p.K;
@@ -235,12 +260,36 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   for (int q = tid; q < M - 1; q += nt) { c_N[q] = p.N[q]; c_lvl[q] = p.lvl[q]; }
   __syncthreads();
 
-  const uint32_t g = blockIdx.x * (uint32_t)nt + tid;        // instances per call < 2^31 (mjp_upload)
+  // ---- which instances this CTA runs ----
+  // Normally CTA b runs instances [b nt, (b+1) nt) from start (or from the park) to the end (or to the slice
+  // boundary).  ROTATION (SLICE variants, p.rot_slices > 0; batches a little larger than what fits on the GPU at
+  // once): the run is cut into p.rot_slices slices of sim time and the resident CTAs pull (chunk of nt instances,
+  // slice) items from a queue -- restore, advance one slice, park -- so that every lane does the same share of the
+  // work instead of the last, partly filled wave costing a full pass.  Slice k of a chunk waits for slice k-1 of
+  // the same chunk (rot_flags, release/acquire); items are handed out slice-major, so the wait is almost never real.
+  __shared__ uint32_t s_rot_item;
   const uint32_t n_inst = (uint32_t)p.n_inst;
+  for (;;) {
+  const bool rotate = SLICE && p.rot_slices > 0;
+  uint32_t chunk = blockIdx.x, rot_k = 0;
+  if (rotate) {
+    __syncthreads();                                         // the previous item's shared slots are no longer in use
+    if (tid == 0) s_rot_item = atomicAdd(p.rot_queue, 1u);
+    __syncthreads();
+    const uint32_t item = s_rot_item;
+    if (item >= p.rot_chunks * (uint32_t)p.rot_slices) break;
+    chunk = item % p.rot_chunks; rot_k = item / p.rot_chunks;
+    if (rot_k > 0) {
+      if (tid == 0) while (ld_acquire_u32(p.rot_flags + chunk) < rot_k) nano_sleep(200);
+      __syncthreads();
+    }
+  }
+  const uint32_t g = chunk * (uint32_t)nt + tid;             // instances per call < 2^31 (mjp_upload)
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
   bool active = g < n_inst;
   // A resumed launch continues exactly the instances that were parked at the previous slice boundary.
-  const bool resume = SLICE && p.resume != 0;
+  const bool resume = SLICE && (rotate ? rot_k > 0 : p.resume != 0);
+  const double slice_until = (rotate && rot_k + 1 < (uint32_t)p.rot_slices) ? p.rot_dt * (double)(rot_k + 1) : p.slice_until;
   if (resume && active && p.status[g] != MJP_INST_PAUSED) active = false;
   const bool fresh_start = active && !resume;
   const bool ran = active;                      // this lane simulates an instance in this launch
@@ -261,9 +310,14 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
 #define TICKCLK    sf[(hb) * nt]                /* :clk of the messages in :log-buf   */
 #define EJENT      sf[(hb + 1) * nt]            /* :ent of this tick's :ej            */
 #define TMINUD     sf[(hb + 2) * nt]            /* earliest pending up/down time (cache) */
-#define ENDS_S(i)  sf[(hb + 3 + (i)) * nt]      /* :status :ends, or remaining work (MT == 0 only) */
-#define GMINE(gr)     sf[(hb + 3 + M + (gr)) * nt]      /* MT == 0: min :ends over the tracked machines of group gr   */
-#define GMINU(gr)     sf[(hb + 3 + M + G + (gr)) * nt]  /* MT == 0: min pending up/down time over group gr            */
+  // :ends (MT == 0): with the per-group minima below it is read only when a group is re-scanned, so the widest
+  // lines (64-bit masks) keep it in the cold scratch too -- it was over half of their shared memory (M = 50:
+  // 732 -> 332 bytes per instance, 4 -> 7 CTAs per SM)
+  constexpr bool ENDS_COLD = COLD && sizeof(MaskT) == 8;
+  const int hg = hb + 3 + (ENDS_COLD ? 0 : M);             // first group-minimum slot
+#define ENDS_S(i)  (*(ENDS_COLD ? &cfp[(5 * M - 1 + (i)) * cs] : &sf[(hb + 3 + (i)) * nt]))   /* :status :ends, or remaining work (MT == 0 only) */
+#define GMINE(gr)  sf[(hg + (gr)) * nt]          /* MT == 0: min :ends over the tracked machines of group gr   */
+#define GMINU(gr)  sf[(hg + G + (gr)) * nt]      /* MT == 0: min pending up/down time over group gr            */
 #define FUT_N(i)   cup[(i) * cs]                 /* :future index                      */
 #define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
 #define CNT(b)     su[(hu + (b)) * nt]          /* bits 0-7 (count :holding) of buffer b; bits 8-18 this tick's
@@ -292,8 +346,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   auto mu_of = [&](int i) -> double { return (p.mu_i != nullptr) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
   auto cap_of = [&](int b) -> int { return (flags & F_CAPPL) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
   auto dur_of = [&](int k, int i) -> double {
-    if (p.dur_i != nullptr) return p.dur_i[(size_t)(k * M + i) * n_inst + g];   // job-requires, divided once at upload
     if (flags & F_DURPL) {
+      if (p.dur_i != nullptr) return p.dur_i[(size_t)(k * M + i) * n_inst + g];   // job-requires, divided once at upload
       const double wv = p.w_i ? p.w_i[(size_t)(k * M + i) * n_inst + g] : p.w[k * M + i];
       const double Wv = p.W_i ? p.W_i[(size_t)i * n_inst + g] : p.W[i];
       return __ddiv_rn(wv, Wv);
@@ -381,16 +435,20 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   for (int b = 0; fresh_start && b < M - 1; ++b) LASTCLK(b) = p.warm_up;
   for (int b = 0; fresh_start && b < M - 1; ++b) CNT(b) = (uint32_t)cap_of(b) << 24;   // :N <= 254 (mjp_upload)
   // Wide lines (MT == 0): the two minima a micro-step needs -- the earliest strictly-future :ends among the
-  // machines that own an :ends candidate, and the earliest pending up/down time -- are kept per GROUP of 8
+  // machines that own an :ends candidate, and the earliest pending up/down time -- are kept per GROUP of GS
   // machines (GMINE / GMINU) and maintained incrementally, so that no pass over all M machines is left on the
   // per-micro-step path: a group is re-read only when its minimum is consumed or a member leaves it.
-  const int G = (M + 7) >> 3;
-  auto grp_bits = [&](MaskT m, int gr) -> uint32_t { return (uint32_t)(m >> (8 * gr)) & 0xFFu; };
-  // min of :ends over the machines `members` (a byte: bit j = machine 8 gr + j) of group gr
+  // Group size GS: 4 machines up to 32 machines, 8 beyond (at most 8 groups either way): a rescan reads GS values
+  // at a few active lanes, the per-micro-step min reads G values at all lanes -- about sqrt(M) each is the balance.
+  constexpr int GSH = sizeof(MaskT) == 4 ? 2 : 3, GS = 1 << GSH;
+  constexpr uint32_t GSM = (1u << GS) - 1u;
+  const int G = (M + GS - 1) >> GSH;
+  auto grp_bits = [&](MaskT m, int gr) -> uint32_t { return (uint32_t)(m >> (GS * gr)) & GSM; };
+  // min of :ends over the machines `members` (bit j = machine GS gr + j) of group gr
   auto group_min_ends = [&](int gr, uint32_t members) -> double {
     double acc = INF;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if ((members >> j) & 1u) { const double e = ENDS_S(8 * gr + j); acc = e < acc ? e : acc; }
+    for (int j = 0; j < GS; ++j) if ((members >> j) & 1u) { const double e = ENDS_S(GS * gr + j); acc = e < acc ? e : acc; }
     return acc;
   };
   // min over the machines' pending up/down times and who attains it: changes only when one fires (MT > 0)
@@ -411,7 +469,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       double t0 = INF;
       for (int gr = 0; gr < G; ++gr) {
         double acc = INF;
-        for (int i = 8 * gr; i < 8 * gr + 8 && i < M; ++i) { const double t = FUT_T(i); acc = t < acc ? t : acc; }
+        for (int i = GS * gr; i < GS * gr + GS && i < M; ++i) { const double t = FUT_T(i); acc = t < acc ? t : acc; }
         GMINU(gr) = acc; GMINE(gr) = INF;
         t0 = acc < t0 ? acc : t0;
       }
@@ -467,13 +525,16 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
   // Kept in the count word: bits 8-15 the level of the FIRST message, bit 16 = it was the :bj, bit 17 = one
   // message so far, bit 18 = two (the second one's level follows: a :sm after a :bj sees one job more, a :bj
   // after a :sm one less).  Stale bits of an older tick are overwritten by the first message of a new one.
-  auto buffer_tick_bits = [&](uint32_t w, MaskT bbit, int n, bool is_bj) -> uint32_t {
+  // Lines of up to 8 machines (MT > 0) can never have more than 8 groups: there the winner is decided right away
+  // (`precedes`: this message's machine comes first) and bits 8-15 simply hold the winning level.
+  auto buffer_tick_bits = [&](uint32_t w, MaskT bbit, int n, bool is_bj, bool precedes) -> uint32_t {
     if (!(touched & bbit)) {
       touched |= bbit;
       return (w & 0xFF000000u) | ((uint32_t)n << 8) | (is_bj ? 0x10000u : 0u) | 0x20000u;
     }
-    const uint32_t hi = w & 0xFFFFFF00u;
+    uint32_t hi = w & 0xFFFFFF00u;
     if ((((hi >> 16) & 1u) != 0) == is_bj || (hi & 0x40000u)) flags |= F_OVF;   // same kind twice, or a third message
+    if (MT > 0 && precedes) hi = (hi & 0xFFFF00FFu) | ((uint32_t)n << 8);
     return hi | 0x40000u;
   };
   auto toggle = [&](MaskT &par, MaskT &two, MaskT bit) {
@@ -616,7 +677,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       const int b = MO::ffs(q); q &= q - 1;
       const uint32_t cw = CNT(b);
       int n = (int)((cw >> 8) & 0xFFu);
-      if (cw & 0x40000u) {
+      if (MT == 0 && (cw & 0x40000u)) {
         const bool first_bj = (cw & 0x10000u) != 0, bj_wins = ((bj_first >> b) & 1) != 0;
         n += (first_bj == bj_wins) ? 0 : (first_bj ? 1 : -1);
       }
@@ -642,13 +703,27 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       flags &= ~(uint32_t)F_EJ;
     }
   };
+  // MT == 0: a job whose :ends v has just become known is entered into its group's minimum right away -- nearly
+  // always the machine owns an :ends candidate in the next micro-step; when it does not (a :BBS machine behind a
+  // full buffer) the membership check at the top of the loop takes it out again and re-reads the group
+  auto track = [&](int i, double v) {
+    if (v > clock) {
+      const int gr = i >> GSH;
+      const double cur = GMINE(gr);
+      GMINE(gr) = v < cur ? v : cur;
+      tracked |= MJP_BIT(i);
+    }
+  };
   // end-time at job start (core.clj:138-151), lazily: fits in the current up interval, or pending
   auto start_job = [&](int i, int type) {
     const MaskT bit = MJP_BIT(i);
     double v;
     if (end_time_begin((up & bit) != 0, FUT_T(i), clock, dur_of(type, i), v)) pend |= bit; else pend &= ~bit;
     set_end(i, v);
-    if (MT == 0) late &= ~bit;                              // a new job: not over, not tracked yet
+    if (MT == 0) {
+      late &= ~bit;                                         // a new job: not over
+      if (!(pend & bit)) track(i, v);
+    }
   };
 
   // ---- time slicing: the complete per-instance state, parked in HBM as [word][instance] ----
@@ -723,7 +798,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       if (!((p.run_to_job >= 0 && (long long)curjob <= p.run_to_job) || (clock <= p.run_to))) {
         finish(MJP_INST_NORMAL_END); live = false;
       } else if (n_ev > 0xC0000000u) { finish(MJP_INST_ITER_LIMIT); live = false; }   // watchdog, see flush_tick
-      else if (SLICE && clock > p.slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
+      else if (SLICE && clock > slice_until) { flags |= F_PAUSE; live = false; }   // slice boundary, between two micro-steps
     }
 
     // new-job core.clj:328-340: keep at least one drawn job type per lane (see tq); here, before the guards,
@@ -776,15 +851,15 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       const MaskT fut0 = cand & ~late;
       uint32_t gdirty = 0;
       for (MaskT q = live ? (tracked & ~fut0) : (MaskT)0; __any_sync(am, q != 0);) if (q) {
-        const int gr = MO::ffs(q) >> 3;
-        q &= ~((MaskT)0xFFu << (8 * gr));
+        const int gr = MO::ffs(q) >> GSH;
+        q &= ~((MaskT)GSM << (GS * gr));
         gdirty |= 1u << gr;                                  // a member left: the group's minimum is re-read below
       }
       for (MaskT q = live ? (fut0 & ~tracked) : (MaskT)0; __any_sync(am, q != 0);) if (q) {
         const int i = MO::ffs(q); q &= q - 1;
         const double e = ENDS_S(i);
         if (clock >= e) late |= MJP_BIT(i);                  // already over: a "now" candidate, never tracked
-        else { const int gr = i >> 3; const double cur = GMINE(gr); GMINE(gr) = e < cur ? e : cur; }
+        else { const int gr = i >> GSH; const double cur = GMINE(gr); GMINE(gr) = e < cur ? e : cur; }
       }
       if (live) tracked = cand & ~late;
       for (uint32_t q = gdirty; __any_sync(am, q != 0);) if (q) {
@@ -838,12 +913,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         uint32_t hit = 0;
         double acc = INF;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if ((members >> j) & 1u) {
-          const double e = ENDS_S(8 * gr + j);
+        for (int j = 0; j < GS; ++j) if ((members >> j) & 1u) {
+          const double e = ENDS_S(GS * gr + j);
           if (e == tstar) hit |= 1u << j; else acc = e < acc ? e : acc;
         }
         GMINE(gr) = acc;
-        m_f |= (MaskT)hit << (8 * gr);
+        m_f |= (MaskT)hit << (GS * gr);
       }
       tracked &= ~m_f;
       late |= m_f;                                            // (every use of the pre-advance `late` is above)
@@ -857,12 +932,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         uint32_t hit = 0;
         double acc = INF;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (8 * gr + j < M) {
-          const double t = FUT_T(8 * gr + j);
+        for (int j = 0; j < GS; ++j) if (GS * gr + j < M) {
+          const double t = FUT_T(GS * gr + j);
           if (t == tstar && !((is_dup >> j) & 1u)) hit |= 1u << j; else acc = t < acc ? t : acc;
         }
         GMINU(gr) = acc;
-        m_ud |= (MaskT)hit << (8 * gr);
+        m_ud |= (MaskT)hit << (GS * gr);
       }
     }
     const MaskT keep = live ? ~(MaskT)0 : (MaskT)0, keep_now = (live && now_any) ? ~(MaskT)0 : (MaskT)0;
@@ -981,11 +1056,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
           FUT_T(i) = t_next; FUT_N(i) = n + 1; up ^= bit;
           if (was_up_event && (pend & bit)) {                // end-time resumes at this :up  core.clj:145-151
             double v;
-            if (!end_time_resume(t_fire, t_next, get_end(i), v)) pend &= ~bit;
+            const bool still = end_time_resume(t_fire, t_next, get_end(i), v);
+            if (!still) pend &= ~bit;
             set_end(i, v);
+            if (MT == 0 && !still) track(i, v);
           }
           if (MT > 0) rescan_fut();
-          else { const int gr = i >> 3; const double cur = GMINU(gr); GMINU(gr) = t_next < cur ? t_next : cur; }
+          else { const int gr = i >> GSH; const double cur = GMINU(gr); GMINU(gr) = t_next < cur ? t_next : cur; }
         }
       }
       if (MT == 0 && __any_sync(am, (b_ud & ~dup_before) != 0)) {
@@ -1006,7 +1083,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_BJ | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_BJ, i, n, id);
-        CNT(i) = (uint32_t)(n + 1) | buffer_tick_bits(cw, bit, n, true);
+        CNT(i) = (uint32_t)(n + 1) | buffer_tick_bits(cw, bit, n, true, ((lead >> i) & 1) != 0);
         if (n + 1 == (int)(cw >> 24)) full |= bit;
         empty &= ~(bit << 1);
       } else {
@@ -1032,7 +1109,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
       if (HASH) { hmix(h, (uint64_t)MJP_ACT_SM | ((uint64_t)i << 8) | ((uint64_t)n << 16) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, 0); }
       mark_seen(i);
       if (LOG) stage_msg(MJP_ACT_SM, i, n, id);
-      CNT(b) = (uint32_t)(n - 1) | buffer_tick_bits(cw, bbit, n, false);
+      CNT(b) = (uint32_t)(n - 1) | buffer_tick_bits(cw, bbit, n, false, ((lead >> b) & 1) == 0);
       if (n - 1 == 0) empty |= bit;
       full &= ~bbit;
       occ |= bit; STARTED(i) = id;
@@ -1077,20 +1154,26 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : 5) mjp_line_kern
     }
     active = live;
   }
-  if (!ran) return;
-  atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
-  n_ev = 0;
-  if (SLICE && (flags & F_PAUSE)) {               // park the untouched state (the lane idled since the boundary)
-    flags &= ~(uint32_t)F_PAUSE;
-    park_save();
-    finish(MJP_INST_PAUSED);
-  }
-  if (flags >> 8) p.status[g] = (uint8_t)((flags >> 8) - 1);
+  if (ran) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(p.n_events) + g, (unsigned long long)n_ev);
+    n_ev = 0;
+    if (SLICE && (flags & F_PAUSE)) {               // park the untouched state (the lane idled since the boundary)
+      flags &= ~(uint32_t)F_PAUSE;
+      park_save();
+      finish(MJP_INST_PAUSED);
+    }
+    if (flags >> 8) p.status[g] = (uint8_t)((flags >> 8) - 1);
 
-  // the reference never flushes the last tick: whatever is still in :log-buf is lost
-  if (p.final_clock) p.final_clock[g] = clock;
-  if (p.curjob) p.curjob[g] = (long long)curjob;
-  if (HASH && p.hash) p.hash[g] = h;
+    // the reference never flushes the last tick: whatever is still in :log-buf is lost
+    if (p.final_clock) p.final_clock[g] = clock;
+    if (p.curjob) p.curjob[g] = (long long)curjob;
+    if (HASH && p.hash) p.hash[g] = h;
+  }
+  if (!rotate) break;
+  __threadfence();                                           // this slice's park / status / scratch before the flag
+  __syncthreads();
+  if (tid == 0) st_release_u32(p.rot_flags + chunk, rot_k + 1);
+  }   // for (;;) over work items
 #undef FUT_T
 #undef ENDS_S
 #undef GMINE

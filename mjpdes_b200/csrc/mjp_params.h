@@ -39,6 +39,12 @@ struct KParams {
   int32_t resume;         // 1: continue the instances parked by the previous launch
   int32_t park_words;     // rows of `park`
   uint32_t *park;         // [park_words][n_inst] parked per-instance state
+  // rotation (see mjp_line_kernel.cuh): resident CTAs pull (chunk, slice) items; 0 slices = off
+  int32_t rot_slices;     // slices of sim time the run is cut into
+  uint32_t rot_chunks;    // chunks of blockDim instances
+  double rot_dt;          // slice k ends at (k+1) rot_dt; the last one at slice_until
+  uint32_t *rot_queue;    // [1] next item
+  uint32_t *rot_flags;    // [rot_chunks] slices completed per chunk
   // MJP_RNG_TAPE: recorded draws, instance-major (nullptr: draw from the Philox substreams)
   const double *tape_jt, *tape_u, *tape_e;
   uint32_t tape_len_jt, tape_len_u, tape_len_e, tape_pad;

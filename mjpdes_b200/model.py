@@ -420,12 +420,12 @@ def main_loop(model: dict, handle=None, out_stream=None, seed: int = DEFAULT_SEE
     wall = time.time() - start
     results = [postprocess_model(cl, res.stats, g, g if n > 1 else 1, wall, log=res.log) for g in range(n)]
     if out_stream is not None:
-        out_stream.write("#_" + scada.pprint_edn(scada.pretty_model(model)) + "\n")      # core.clj:751-752,774-775
+        out_stream.write("#_" + scada.pprint_edn(scada.pretty_model(model), print_length=10) + "\n")   # core.clj:750-752,773-775
         if res.log is not None:
             for text in scada.render_lines(cl, res.log):
                 out_stream.write(text + "\n")
         for r in results:                                                                 # util/log.clj:305-319
-            out_stream.write("#_" + scada.pprint_edn({k: v for k, v in r.items() if k != ":jobmix"}) + "\n")
+            out_stream.write(scada.result_block(r) + "\n")
     return results[0] if n == 1 else results
 
 

@@ -7,8 +7,7 @@
   pretty-model        util/log.clj:293-303
 
 The device emits compact binary records (mjp_log_record); this module is the host-side
-"next" row of SURVEY.md 8(f).  Result / model maps are printed as EDN with one key per line;
-the reference's clojure.pprint line-breaking is not reproduced byte for byte.
+"next" row of SURVEY.md 8(f).  Result / model maps are laid out as clojure.pprint does (pprint_edn), keys in Clojure map order.
 """
 from __future__ import annotations
 
@@ -107,27 +106,216 @@ def pull_data(cl, records: np.ndarray, n: int | None, instance: int = 0):
     return [message_map(cl, r) for r in recs]
 
 
+# defrecord field lists (core.clj:38-66): a record prints its declared fields first, in this order and nil when unset,
+# then whatever else was put into it
+RECORD_FIELDS = {"Model": [":line", ":entry-point", ":jobmix", ":params", ":topology", ":print"],
+                 "ExpoMachine": [":name", ":lambda", ":mu", ":status", ":W", ":up&down"],
+                 "Buffer": [":N", ":holding"], "JobType": [":w"]}
+_PRETTY_DROPS = (":name", ":status", ":mchain", ":up&down", ":holding")          # util/log.clj:300
+
+
+def clj_order(x, force_hash: bool = False):
+    """`x` with every map re-keyed in the order Clojure would iterate (and so print) it: records by declared
+    fields then extras; plain maps in insertion order up to 8 entries and in hash order beyond (cljhash.py).
+    ``force_hash``: the top-level map was a hash map once (it held more than 8 entries) and stayed one."""
+    from . import cljhash
+    if isinstance(x, dict):
+        tag = getattr(x, "tag", None)
+        if tag in RECORD_FIELDS:
+            basis = RECORD_FIELDS[tag]
+            keys = basis + cljhash.map_order([k for k in x if k not in basis])
+            return {k: clj_order(x.get(k)) for k in keys}
+        keys = list(x.keys())
+        if force_hash:
+            keys = sorted(keys, key=lambda k: cljhash.trie_key(cljhash.keyword_hash(k)))
+        elif all(isinstance(k, str) and k.startswith(":") for k in keys):
+            keys = cljhash.map_order(keys)
+        return {k: clj_order(x[k]) for k in keys}
+    if isinstance(x, (list, tuple)):
+        return [clj_order(v) for v in x]
+    return x
+
+
 def pretty_model(model: dict) -> dict:
-    """util/log.clj:293-303: drop :name :status :mchain :up&down :holding from the equipment."""
-    out = dict(model)
-    out[":line"] = {k: {a: b for a, b in dict(v).items() if a not in (":name", ":status", ":mchain", ":up&down", ":holding")}
-                    for k, v in model[":line"].items()}
+    """util/log.clj:293-303: drop :name :status :mchain :up&down :holding from the equipment (dissoc of a declared
+    field turns the record into a plain map of its remaining fields, in field order), everything in print order."""
+    from . import cljhash
+    line = model[":line"]
+    pretty_line = {}
+    for name in cljhash.map_order(list(line.keys())):
+        equip = clj_order(line[name]) if getattr(line[name], "tag", None) in RECORD_FIELDS else dict(line[name])
+        pretty_line[name] = {a: clj_order(b) for a, b in equip.items() if a not in _PRETTY_DROPS}
+    out = clj_order(model)
+    out[":line"] = pretty_line
     return out
 
 
-def pprint_edn(x, indent: int = 0) -> str:
-    pad = " " * (indent + 1)
-    if isinstance(x, dict):
-        if not x:
-            return "{}"
-        items = [f"{k} {pprint_edn(v, indent + len(str(k)) + 2)}" for k, v in x.items()]
-        return "{" + (",\n" + pad).join(items) + "}"
-    if isinstance(x, (list, tuple)):
-        return "[" + " ".join(pprint_edn(v, indent + 1) for v in x) + "]"
+RESULT_KEYS = (":runtime", ":TP", ":observed-residence-time", ":number-of-jobs", ":blocked", ":starved",
+               ":avg-buffer-occupancy", ":bottleneck-machine", ":process-id", ":diag-log-buf", ":status")
+
+
+def result_block(res: dict) -> str:
+    """The ``#_`` result block of one simulation as output-sims / main-loop-once print it (util/log.clj:305-319,
+    core.clj:785-786): the reference's own keys (no README aliases, :jobmix dissoc'ed), in the order of the hash map
+    the result became when its ninth key was assoc'ed (core.clj:711-718); :TP is a float (core.clj:625);
+    *print-length* is 10 (core.clj:750,773)."""
+    shown = {k: res[k] for k in RESULT_KEYS if k in res}
+    if ":TP" in shown:
+        shown[":TP"] = np.float32(shown[":TP"])
+    return "#_" + pprint_edn(clj_order(shown, force_hash=True), print_length=10)
+
+
+RIGHT_MARGIN = 72          # clojure.pprint/*print-right-margin*
+
+
+def java_float(x) -> str:
+    """Float/toString: what Clojure prints for ``(float ...)`` (:TP, core.clj:625)."""
+    f = np.float32(x)
+    if f == 0:
+        return "0.0"
+    a = abs(float(f))
+    digits = np.format_float_scientific(f, unique=True, trim="0")        # shortest digits that round-trip as a float
+    mant, exp = digits.split("e")
+    if 1e-3 <= a < 1e7:
+        return np.format_float_positional(f, unique=True, trim="0")
+    return f"{mant}E{int(exp)}"
+
+
+def _atom(x) -> str:
     if isinstance(x, bool):
         return "true" if x else "false"
     if x is None:
         return "nil"
-    if isinstance(x, float):
-        return java_double(x)
+    if isinstance(x, np.float32):
+        return java_float(x)
+    if isinstance(x, (float, np.floating)):
+        return java_double(float(x))
+    if isinstance(x, (int, np.integer)):
+        return str(int(x))
+    if isinstance(x, str) and not x.startswith(":") and not getattr(x, "is_symbol", False) and type(x) is str:
+        return '"' + x.replace("\\", "\\\\").replace('"', '\\"') + '"'
     return str(x)
+
+
+class _More:
+    """What clojure.pprint writes in place of the elements beyond *print-length*."""
+
+    def __repr__(self):
+        return "..."
+
+
+_MORE = _More()
+
+
+def _entries(x, limit):
+    """(key, value) pairs of a map, cut at *print-length* (the cut shows as a bare ``...``)."""
+    items = list(x.items())
+    if limit is not None and len(items) > limit:
+        return items[:limit] + [(_MORE, _MORE)]
+    return items
+
+
+def _elements(x, limit):
+    items = list(x)
+    if limit is not None and len(items) > limit:
+        return items[:limit] + [_MORE]
+    return items
+
+
+def _flat(x, limit=None) -> str:
+    """The one-line rendering (what clojure.pprint produces when everything fits)."""
+    if isinstance(x, dict):
+        return "{" + ", ".join("..." if k is _MORE else f"{_flat(k, limit)} {_flat(v, limit)}" for k, v in _entries(x, limit)) + "}"
+    if isinstance(x, (list, tuple)):
+        return "[" + " ".join(_flat(v, limit) for v in _elements(x, limit)) + "]"
+    if x is _MORE:
+        return "..."
+    return _atom(x)
+
+
+def pprint_edn(x, col: int = 0, trailing: int = 0, print_length: int | None = None) -> str:
+    """``clojure.pprint/pprint`` of maps, vectors and atoms, laid out as the reference's ``#_`` blocks are
+    (core.clj:774-775,785-786, util/log.clj:305-319).
+
+    Restated from clojure.pprint (pprint-map / pprint-vector, pretty_writer.clj; Clojure 1.9): a map is a logical
+    block ``{ ... }`` whose entries are separated by ``", "`` + a :linear conditional newline; every entry is its own
+    block ``key`` + space + :linear newline + ``value``; a vector has a :linear newline after every element.  A
+    :linear newline of block B is taken iff B already had a line break inside it, or the text from the newline up
+    to the next conditional newline of an ENCLOSING block (so: through the end of B and any closing brackets and
+    separators that follow) does not fit before column 72 (``column + length < 72``).  Continuation lines of a
+    block start in the column after its opening bracket; an entry's value that is pushed to its own line starts in
+    the column of the entry's key.  Pinned on the reference's recorded outputs (``data/new-out.clj``,
+    ``data/out-10.clj``, ``data/submodel-1-out.clj``): re-printing the parsed files reproduces them byte for byte
+    (tests/test_host_model.py).  ``col``: column the value starts in; ``trailing``: characters that follow it
+    before the next newline opportunity of an enclosing block; ``print_length``: ``*print-length*`` (the reference
+    binds it to 10 around its ``#_`` blocks, core.clj:750,773: longer collections end in ``...``)."""
+    return _pp(x, col, trailing, print_length)[0]
+
+
+def _pp(x, col: int, trailing: int, limit=None):
+    """-> (text, a line break was emitted inside)"""
+    flat = _flat(x, limit)
+    fits = lambda c, n: c + n < RIGHT_MARGIN
+    if isinstance(x, dict) and x:
+        items = _entries(x, limit)
+        indent = col + 1
+        out, cur, broke = "{", indent, False
+        # flat lengths of the entries still to come (with their separators), for the map-level newlines
+        flats = [3 if k is _MORE else len(_flat(k, limit)) + 1 + len(_flat(v, limit)) for k, v in items]
+        for idx, (k, v) in enumerate(items):
+            last = idx == len(items) - 1
+            if k is _MORE:                                               # always the last one
+                out += "..."
+                break
+            ktxt = _flat(k, limit)
+            entry_col = cur
+            etrail = (1 + trailing) if last else 2                       # "}" + what follows the map, or ", "
+            out += ktxt + " "
+            cur += len(ktxt) + 1
+            if fits(cur, len(_flat(v, limit)) + etrail):                  # the entry's own :linear newline
+                vtxt, vbroke = _flat(v, limit), False
+                out += vtxt
+                cur += len(vtxt)
+            else:
+                out = out[:-1] + "\n" + " " * entry_col                  # (trailing white space is dropped at a break)
+                vtxt, _ = _pp(v, entry_col, etrail, limit)
+                out += vtxt
+                cur = len(vtxt.rsplit("\n", 1)[-1]) + (entry_col if "\n" not in vtxt else 0)
+                broke = True
+            if not last:
+                out += ","
+                rest = sum(flats[idx + 1:]) + 2 * (len(items) - idx - 2) + 1 + trailing   # entries, ", " between, "}" + after
+                if broke or not fits(cur + 2, rest):
+                    out += "\n" + " " * indent
+                    cur = indent
+                    broke = True
+                else:
+                    out += " "
+                    cur += 2
+        return out + "}", broke
+    if isinstance(x, (list, tuple)) and len(x):
+        indent = col + 1
+        out, cur, broke = "[", indent, False
+        x = _elements(x, limit)
+        flats = [len(_flat(v, limit)) for v in x]
+        for idx, v in enumerate(x):
+            last = idx == len(x) - 1
+            vtrail = (1 + trailing) if last else 1
+            if isinstance(v, (dict, list, tuple)) and not fits(cur, flats[idx] + vtrail):
+                vtxt, vb = _pp(v, cur, vtrail, limit)
+                broke = broke or vb
+            else:
+                vtxt = _flat(v, limit)
+            out += vtxt
+            cur = len(vtxt.rsplit("\n", 1)[-1]) + (cur if "\n" not in vtxt else 0)
+            if not last:
+                rest = sum(flats[idx + 1:]) + (len(x) - idx - 2) + 1 + trailing
+                if broke or not fits(cur + 1, rest):
+                    out += "\n" + " " * indent
+                    cur = indent
+                    broke = True
+                else:
+                    out += " "
+                    cur += 1
+        return out + "]", broke
+    return flat, False

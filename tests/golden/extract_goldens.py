@@ -15,6 +15,7 @@ package's EDN reader -- nothing is typed by hand:
   G6     core_test.clj:199-247  calc-bneck tables tp1 -> :m4, tp2 -> :m2
   G7     core_test.clj:251-287  load-m1 model and its 15 expected messages
   G8/G9  log_test.clj:17-77     reliable BAS / BBS models, 6-tuples, spans
+  G11    data/*-out.clj         recorded result blocks as printed text (hash-map key order, pprint layout)
 """
 import json
 import os
@@ -159,6 +160,26 @@ def main():
     # recorded outputs quoted by SURVEY.md 6 (loose statistical sanity only; :blocked excluded)
     out["recorded"] = {"data/new-out.clj": plain(edn.read_file(os.path.join(REF, "data/new-out.clj"))),
                        "data/ex1-out-out.clj": plain(edn.read_file(os.path.join(REF, "data/ex1-out-out.clj")))}
+
+    # G11: the recorded outputs as TEXT.  They were printed by clojure.pprint from 11-entry result maps, so they pin
+    # (a) the iteration order of a Clojure hash map of keywords (cljhash.py: the keys appear in exactly that order)
+    # and (b) clojure.pprint's layout and Java's double formatting (scada.pprint_edn re-prints them byte for byte).
+    def head_forms(rel, k):
+        text = open(os.path.join(REF, rel)).read()
+        blocks, depth, start = [], 0, None
+        for pos, ch in enumerate(text):
+            if ch == "{":
+                if depth == 0:
+                    start = pos
+                depth += 1
+            elif ch == "}":
+                depth -= 1
+                if depth == 0:
+                    blocks.append(text[start:pos + 1])
+        return blocks[:k]
+    out["G11"] = {"cite": "data/new-out.clj, data/ex1-out-out.clj, data/out-10.clj:1-54, data/submodel-1-out.clj:1-22",
+                  "printed": head_forms("data/new-out.clj", 1) + head_forms("data/ex1-out-out.clj", 1) +
+                             head_forms("data/out-10.clj", 2) + head_forms("data/submodel-1-out.clj", 2)}
 
     path = os.path.join(HERE, "reference_goldens.json")
     with open(path, "w") as fh:

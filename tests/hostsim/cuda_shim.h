@@ -26,6 +26,8 @@ alignas(16) unsigned char smem_raw[1 << 20];
 alignas(16) double red[4096];
 }
 static inline void __syncthreads() {}
+static inline void __threadfence() {}
+static inline unsigned atomicAdd(unsigned *a, unsigned v) { unsigned o = *a; *a = o + v; return o; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }

@@ -7,6 +7,11 @@
 #include <limits>
 #include <vector>
 
+// Rotation (mjp_line_kernel.cuh): > 0 makes the next runs pull (chunk, slice) items from the work queue.  With one
+// thread per block a single "CTA" drains the whole queue in order, which exercises restore / advance / park per item.
+static int g_rot_slices = 0;
+extern "C" void hostsim_set_rotation(int slices) { g_rot_slices = slices; }
+
 // One launch per slice boundary in `slices` (then one to the end), resuming the parked state each time.
 extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
                                   int want_hash, mjp_log_out *log, int force_cold, const double *slices, int n_slices,
@@ -26,7 +31,13 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   kp.by_rank = pl.by_rank.data();
   kp.lam_i = L->lambda_inst; kp.mu_i = L->mu_inst; kp.W_i = L->W_inst; kp.w_i = L->w_inst; kp.N_i = L->N_inst;
   const bool want_log_early = log && L->log;
-  const bool sweep = n_slices > 0;     // template slot 5 is SLICE; override planes are a run-time check
+  const bool rot = g_rot_slices > 0 && n_slices == 0;
+  const bool sweep = n_slices > 0 || rot;     // template slot 5 is SLICE; override planes are a run-time check
+  std::vector<uint32_t> rotbuf(n_inst + 1, 0u);
+  if (rot) {
+    kp.rot_slices = g_rot_slices; kp.rot_chunks = (uint32_t)n_inst; kp.rot_dt = kp.run_to / g_rot_slices;
+    kp.rot_queue = rotbuf.data(); kp.rot_flags = rotbuf.data() + 1;
+  }
   std::vector<double> enters((size_t)kp.R * n_inst);
   kp.enters = enters.data();
   for (size_t q = 0; q < n_inst; ++q) s->status[q] = MJP_INST_NOT_RUN;
@@ -36,7 +47,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   const bool cold = force_cold != 0;
   const bool mt_ok = !cold && M >= 2 && M <= 8;
   mjp::plan_layout(kp, mt_ok, rng->mode != MJP_RNG_COUNTER, want_log_early, cold);
-  std::vector<double> coldf((size_t)mjp::cold_f64_slots(kp) * n_inst);
+  std::vector<double> coldf((size_t)(mjp::cold_f64_slots(kp) + mjp::cold_ends_slots(kp)) * n_inst);
   std::vector<uint32_t> coldu((size_t)mjp::cold_u32_slots(kp, true) * n_inst);
   kp.cold_f = coldf.data(); kp.cold_u = coldu.data();
   kp.njobs = s->njobs; kp.residence = s->residence_sum; kp.blocked = s->blocked_time; kp.starved = s->starved_time;
@@ -55,7 +66,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   for (int sl = 0; sl <= n_slices; ++sl) {
   kp.slice_until = sl < n_slices ? slices[sl] : std::numeric_limits<double>::infinity();
   kp.resume = sl > 0;
-  for (uint64_t g = 0; g < n_inst; ++g) {
+  for (uint64_t g = 0; g < (rot ? 1 : n_inst); ++g) {
     blockIdx.x = (unsigned)g;
 #define RUN3(MK, MT, LG) \
     if (replay && hash && sweep) mjp::mjp_line_kernel<MK, MT, true, true, true, LG>(kp); \

@@ -276,3 +276,33 @@ def test_aggregate_tensor_aliases_the_device_vector(plain):
     t = plain.aggregate_tensor()
     assert t.is_cuda and t.dtype == torch.float64 and t.numel() == abi.aggregate_len(line.M)
     assert np.array_equal(t.cpu().numpy(), plain.download_fields(("aggregate",)).aggregate)
+
+
+# ---- rotation: batches a little larger than one wave ----------------------------------------------------------
+
+@pytest.mark.parametrize("mode", MODES)
+def test_rotation_on_device(plain, oracle, mode):
+    """130 000 instances of example.clj need 1.25 waves of CTAs: the launch rotates them through the resident CTAs
+    ((chunk, slice) work items, release/acquire flags between the slices of a chunk).  Results equal the oracle's."""
+    n = 130_000
+    line = example_line(run_to=200.0, warm_up=20.0)
+    got = plain.run(line, n, mode=mode, seed=SEED, first_instance_id=77).stats
+    want = oracle.run(line, n, mode=mode, seed=SEED, first_instance_id=77, n_threads=CORES).stats
+    same(got, want)
+
+
+def test_rotation_on_device_wide_and_logged(plain, oracle):
+    n = 9472 * 2 + 100                                     # > one wave of the 50-machine COLD layout (6 CTAs/SM)
+    line = long50_line(warm_up=10.0, run_to=60.0)
+    same(plain.run(line, n, seed=5).stats, oracle.run(line, n, seed=5, n_threads=CORES).stats)
+    n = 120_000
+    line = example_line(run_to=120.0, warm_up=60.0, log=True, up_down=True, max_lines=abi.UINT64_MAX)
+    cap = n * 400
+    got = plain.run(line, n, seed=9, log_capacity=cap)
+    want = oracle.run(line, n, seed=9, log_capacity=cap, n_threads=CORES)
+    same(got.stats, want.stats)
+    assert got.rc == abi.OK and len(got.log) == len(want.log)
+    order = lambda r: r[np.argsort((r["instance"].astype(np.uint64) << np.uint64(32)) | r["line"].astype(np.uint64))]
+    a, b = order(got.log), order(want.log)
+    for f in ("instance", "line", "act", "machine", "n", "job", "clk"):
+        assert np.array_equal(a[f], b[f]), f

@@ -271,3 +271,42 @@ def test_streaming_equals_one_shot_capture(engine, oracle):
     want = oracle.run(line, 1, mode=abi.RNG_REPLAY, seed=SEED, log_capacity=100_000)
     ref = scada.pull_data(cl, want.log, 3000)
     assert msgs == ref
+
+
+def test_recorded_outputs_pin_hash_map_order_and_pprint_layout():
+    """G11: the reference's recorded result blocks (data/*-out.clj), as text.  They were printed from 11-entry hash
+    maps: (a) their key order is the iteration order cljhash.py computes for those keywords -- the same order rule
+    the kernel and the oracle apply to ticks with more than 8 machines, to :jobmix beyond 8 job types and to
+    calc-bneck beyond 8 machines; (b) re-printing the parsed block with scada.pprint_edn gives back the text byte
+    for byte (clojure.pprint layout, Double/toString digits)."""
+    from mjpdes_b200 import cljhash, edn, scada
+    printed = GOLDENS["G11"]["printed"]
+    assert len(printed) == 6
+    for text in printed:
+        form = edn.read_string(text)
+        keys = list(form.keys())
+        assert len(keys) == 11
+        assert cljhash.map_order(sorted(keys)) == keys                     # (a)
+        assert scada.pprint_edn(form) == text                              # (b)
+
+
+def test_result_block_and_model_block_follow_the_reference_print_order():
+    from mjpdes_b200 import scada
+    res = {":runtime": 10.823, ":TP": 0.7300555944442749, ":observed-residence-time": 12.205651350281991,
+           ":number-of-jobs": 13141, ":blocked": {":m1": 0.5, ":m2": 0.0}, ":starved": {":m1": 0.0, ":m2": 0.25},
+           ":avg-buffer-occupancy": {":b1": 1.5}, ":bottleneck-machine": ":m1", ":process-id": 1, ":jobmix": {},
+           ":status": ":normal-end", ":average-buffer-occupancy": {":b1": 1.5}, ":bneck": ":m1"}
+    text = scada.result_block(res)
+    assert text.startswith("#_{:TP 0.7300556,\n :number-of-jobs 13141,\n :avg-buffer-occupancy {:b1 1.5},\n :status :normal-end,")
+    assert ":jobmix" not in text and ":bneck" not in text and text.endswith(":process-id 1}")
+    # *print-length* 10 (core.clj:750,773): longer collections are cut
+    long = scada.pprint_edn({":topology": [f":m{i}" for i in range(1, 14)]}, print_length=10)
+    assert long == "{:topology [:m1 :m2 :m3 :m4 :m5 :m6 :m7 :m8 :m9 :m10 ...]}"
+    # the model block: record fields first, in defrecord order and nil when unset (core.clj:38-66); the 9-entry :line
+    # map in hash order; machines reduced to a plain map by pretty-model's dissoc (util/log.clj:293-303)
+    m = as_model(GOLDENS["models"]["resources/example.clj"])
+    block = scada.pprint_edn(scada.pretty_model(m), print_length=10)
+    lines = block.split("\n")
+    assert lines[0] == "{:line" and lines[1] == " {:m5 {:lambda 0.1, :mu 0.9, :W 1.2},"
+    assert lines[-1] == " :print nil}" and " :topology [:m1 :b1 :m2 :b2 :m3 :b3 :m4 :b4 :m5]," in lines
+    assert [l.split()[0] for l in lines if l.startswith(" :")] == [":entry-point", ":jobmix", ":params", ":topology", ":print"]

@@ -182,3 +182,29 @@ def test_fuzz_profiles_sample(oracle):
         for t in range(first, first + 300):
             cpu_fuzz.one(t)
     cpu_fuzz.WILD = False
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_rotation_is_invisible(oracle, mode):
+    """Rotation (the work queue of (chunk, slice) items the SLICE variants can pull from, mjp_line_kernel.cuh): with
+    one thread per block a single "CTA" drains the queue in order, i.e. every instance is restored, advanced one
+    slice and parked per item -- results equal an uninterrupted run, whatever the number of slices."""
+    for line, n, cold in ((example_line(run_to=900.0, warm_up=90.0), 12, False),
+                          (mixed20_line(warm_up=50, run_to=400, log=False), 5, False),
+                          (long50_line(warm_up=50, run_to=300), 4, True),
+                          (example_line(run_to=300.0, warm_up=30.0, run_to_job=500), 7, False)):
+        want = oracle.run(line, n, mode=mode, seed=SEED, n_threads=4).stats
+        for slices in (2, 5, 16):
+            assert_same(H.run(line, n, mode=mode, seed=SEED, cold=cold, rotation=slices), want)
+
+
+def test_rotation_with_scada_log(oracle):
+    line = example_line(run_to=600.0, warm_up=60.0, log=True, up_down=True, max_lines=abi.UINT64_MAX)
+    want = oracle.run(line, 6, seed=SEED, log_capacity=60000)
+    got = H.run(line, 6, seed=SEED, log_capacity=60000, rotation=7)
+    assert_same(got, want.stats)
+    key = lambda r: np.argsort((r["instance"].astype(np.uint64) << np.uint64(32)) | r["line"].astype(np.uint64))
+    a, b = got.log[key(got.log)], want.log[key(want.log)]
+    assert len(a) == len(b) > 30000
+    for f in ("instance", "line", "act", "machine", "n", "job", "clk"):
+        assert np.array_equal(a[f], b[f]), f

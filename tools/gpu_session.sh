@@ -33,6 +33,11 @@ if has ab_persist; then
   done > $O/${TAG}_ab_persist.log 2>&1
   cat $O/${TAG}_ab_persist.log
 fi
+if has cliff; then
+  MJP_ROTATE=0 timeout 600 python tools/cliff_probe.py > $O/${TAG}_cliff_norotate.json 2> $O/${TAG}_cliff_norotate.err; echo "cliff0 exit $?"
+  timeout 600 python tools/cliff_probe.py > $O/${TAG}_cliff_rotate.json 2> $O/${TAG}_cliff_rotate.err; echo "cliff1 exit $?"
+  cat $O/${TAG}_cliff_norotate.json $O/${TAG}_cliff_rotate.json
+fi
 if has ncu_c2; then prof C2_example; fi
 if has ncu_wide; then prof C3_sweep10; prof C4_mixed20_stats_many; prof C5_long50; fi
 if has ncu_c4; then prof C4_mixed20_stats; fi

@@ -18,7 +18,7 @@ def main():
     rows = list(csv.reader(open(sass)))
     hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
     hdr = rows[hi]
-    ie, te = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    ie, te, sm = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
     inst = [r for r in rows[hi + 1:] if len(r) > te]
     lm = N.line_map(SO, mangled)
     assert len(lm) == len(inst), (len(lm), len(inst), "rebuild mismatch: profile and .so differ")
@@ -26,7 +26,8 @@ def main():
     find = lambda s: next(i + 1 for i, l in enumerate(src) if s in l)
     marks = [("prologue/init", 1), ("loop head + guard masks", find("for (;;) {")),
              ("scan (min candidate time)", find("Machines whose job is already over")),
-             ("t*, batch masks", find("const MaskT m_ud = (tmin_ud == tstar)")), ("clock + flush vote", find("// ---- advance-clock")),
+             ("t*, m_f / m_ud (group scans)", find("// future :ends equal to t*")),
+             ("batch masks", find("const MaskT keep = live ?")), ("clock + flush vote", find("// ---- advance-clock")),
              ("AJ section", find("if (__any_sync(am, b_aj != 0))")), ("UP/DOWN section", find("bring-machine-up, then -down")),
              ("TOBUF section", find("// advance2buffer core.clj:285-300")), ("TOMACH section", find("// advance2machine core.clj:263-277")),
              ("record-actions section", find("record-actions core.clj:304-326, in the order")),
@@ -36,7 +37,7 @@ def main():
                ("byte get/set, params", find("auto getb"), find("double r_end[")),
                ("get_end/set_end", find("double r_end["), find("auto px =")),
                ("next_event_time", find("auto next_event_time"), find("// ---- preprocess-model")),
-               ("rescan_fut", find("auto rescan_fut"), find("if (fresh_start) rescan_fut();")),
+               ("group minima helpers / rescan_fut", find("const int G = (M + 7) >> 3;"), find("if (fresh_start) {")),
                ("mark_seen/toggle/type_from", find("auto mark_seen"), find("// ---- SCADA capture")),
                ("job-type draw (whole warp)", find("keep at least one drawn job type"), find("// ---- runables")),
                ("up/down generation (whole warp)", find("Pre-generate the event AFTER"), find("bring-machine-up, then -down")),
@@ -55,12 +56,13 @@ def main():
                 for name, a in marks:
                     if l >= a:
                         key = name
-        x = agg.setdefault(key, [0, 0])
-        x[0] += int(r[ie] or 0); x[1] += int(r[te] or 0)
+        x = agg.setdefault(key, [0, 0, 0])
+        x[0] += int(r[ie] or 0); x[1] += int(r[te] or 0); x[2] += int(r[sm] or 0)
     ti = sum(v[0] for v in agg.values())
-    print(f"{'section':40s} {'% warp-inst':>11s} {'lanes':>6s}" + (f" {'inst/event':>10s}" if events else ""))
+    ts = sum(v[2] for v in agg.values())
+    print(f"{'section':40s} {'% warp-inst':>11s} {'lanes':>6s} {'% samples':>9s}" + (f" {'inst/event':>10s}" if events else ""))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        print(f"{k:40s} {100 * v[0] / ti:10.1f}% {v[1] / max(v[0], 1):6.1f}" + (f" {v[0] / events:10.2f}" if events else ""))
+        print(f"{k:40s} {100 * v[0] / ti:10.1f}% {v[1] / max(v[0], 1):6.1f} {100 * v[2] / max(ts, 1):8.1f}%" + (f" {v[0] / events:10.2f}" if events else ""))
 
 if __name__ == "__main__":
     main()
