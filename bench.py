@@ -268,31 +268,44 @@ def bench_configs(args, cl: Cluster, h, peak_gwis: float, hbm_gbs: float) -> dic
     finish("C4_mixed20_stats_saturated", ms, float(st.n_events.sum()),
            {"scaling": "weak", "instances_per_gpu": n4s, "all_normal_end": bool(np.all(st.status == abi.INST_NORMAL_END)),
             "shape": "M=20 mixed BAS/BBS K=8, statistics only, warm-up 2000, run-to 20000; instance count that fills one GPU"})
-    # SCADA capture over the window 2000..3000 (the full horizon would be 173 GB of records per 10 000 instances):
-    # window time = (run to 3000 with capture) - (the capture-free run to 2000 of the same instances)
-    h.upload(wl.mixed20_line(warm_up=2000.0, run_to=2000.001, log=False, up_down=True), n4)
-    timed_launch(first_instance_id=first4)
-    ms_pre = timed_launch(first_instance_id=first4)
-    ev_pre = float(h.download_fields(("n_events",)).n_events.sum())
-    h.upload(wl.mixed20_line(warm_up=2000.0, run_to=3000.0), n4)
-    h.reserve_log(n4 * 40_000)
-    timed_launch(first_instance_id=first4, want_log=True)
-    ms_log = timed_launch(first_instance_id=first4, want_log=True)
-    ev_log = float(h.download_fields(("n_events",)).n_events.sum())
-    records, dropped = h.log_count()
-    ms_win = cl.reduce(ms_log - ms_pre, "max")
-    rec = cl.reduce(float(records), "sum")
-    ev_win = cl.reduce(ev_log - ev_pre, "sum")
-    bps = 32.0 * rec / (ms_win / 1e3)
-    out["C4_mixed20_scada"] = {
-        "scaling": "weak", "instances_per_gpu": n4, "n_gpus": world, "window": "sim time 2000..3000, :log? true :up&down? true",
-        "records": rec, "dropped": cl.reduce(float(dropped), "sum"), "window_ms": ms_win, "events_in_window": ev_win,
-        "events_per_sec": ev_win / (ms_win / 1e3), "records_per_sec": rec / (ms_win / 1e3), "record_bytes_per_sec": bps,
-        "ms_with_capture_0_to_3000": cl.reduce(ms_log, "max"), "ms_capture_free_0_to_2000": cl.reduce(ms_pre, "max"),
-        "roofline": issue_roofline("C4_mixed20_scada", ev_win / (ms_win / 1e3) / world, peak_gwis),
-        "roofline_writeback": {"bound": "hbm", "achieved": bps / 1e9 / world, "peak": hbm_gbs, "unit": "GB/s",
-                               "frac": bps / 1e9 / world / hbm_gbs, "algorithmic_bytes": 32.0 * rec / world,
-                               "note": "32-byte records over the capture window only, per GPU"}}
+    # SCADA capture over a window after the warm-up (C4's full horizon would be 173 GB of records per 10 000 instances):
+    # window time = (run to the end of the window with capture) - (the capture-free run to 2000 of the same instances)
+    def scada_window(name, mk_line, n, first, t_end, records_per_instance, model, note):
+        h.upload(mk_line(2000.001, False), n)
+        timed_launch(first_instance_id=first)
+        ms_pre = timed_launch(first_instance_id=first)
+        ev_pre = float(h.download_fields(("n_events",)).n_events.sum())
+        h.upload(mk_line(t_end, True), n)
+        h.reserve_log(int(n * records_per_instance))
+        timed_launch(first_instance_id=first, want_log=True)
+        ms_log = timed_launch(first_instance_id=first, want_log=True)
+        ev_log = float(h.download_fields(("n_events",)).n_events.sum())
+        records, dropped = h.log_count()
+        ms_win = cl.reduce(ms_log - ms_pre, "max")
+        rec = cl.reduce(float(records), "sum")
+        ev_win = cl.reduce(ev_log - ev_pre, "sum")
+        ev_all = cl.reduce(ev_log, "sum")
+        bps = 32.0 * rec / (ms_win / 1e3)
+        out[name] = {
+            "scaling": "weak", "instances_per_gpu": n, "n_gpus": world, "window": f"sim time 2000..{t_end:g}, :log? true :up&down? true",
+            "note": note, "records": rec, "dropped": cl.reduce(float(dropped), "sum"), "window_ms": ms_win,
+            "events_in_window": ev_win, "events_per_sec": ev_win / (ms_win / 1e3), "records_per_sec": rec / (ms_win / 1e3),
+            "record_bytes_per_sec": bps,
+            "events_per_sec_whole_run": ev_all / (cl.reduce(ms_log, "max") / 1e3),
+            "ms_with_capture": cl.reduce(ms_log, "max"), "ms_capture_free_0_to_2000": cl.reduce(ms_pre, "max"),
+            "roofline": issue_roofline(model, ev_win / (ms_win / 1e3) / world, peak_gwis),
+            "roofline_writeback": {"bound": "hbm", "achieved": bps / 1e9 / world, "peak": hbm_gbs, "unit": "GB/s",
+                                   "frac": bps / 1e9 / world / hbm_gbs, "algorithmic_bytes": 32.0 * rec / world,
+                                   "note": "32-byte records over the capture window only, per GPU"}}
+
+    c4 = lambda t_end, log: wl.mixed20_line(warm_up=2000.0, run_to=t_end, log=log, up_down=True)
+    scada_window("C4_mixed20_scada", c4, n4, first4, 3000.0, 40_000, "C4_mixed20_scada",
+                 "the named configuration: 10 000 instances (68 lanes per SM: latency-bound)")
+    scada_window("C4_mixed20_scada_saturated", c4, n4s, 10 ** 7 + rank * n4s, 2300.0, 12_500, "C4_mixed20_scada",
+                 "enough instances to fill the GPU; shorter window so that the record stream (25 GB) stays in HBM")
+    ex = lambda t_end, log: wl.example_line(warm_up=2000.0, run_to=t_end, log=log, up_down=True, max_lines=abi.UINT64_MAX)
+    scada_window("example_scada", ex, args.instances, 2 * 10 ** 7 + rank * args.instances, 3000.0, 12_500, "example_scada",
+                 "resources/example.clj with :log? true :up&down? true, 100 000 instances per GPU")
 
     # -- C5: 50 machines, 16 job types: every instance resident, advanced by one sim-time quantum per launch
     n5 = args.c5_instances

@@ -57,6 +57,7 @@ struct KParams {
   int32_t nf64, nu32;     // per-thread slots
   int32_t const_bytes;    // CTA constant table size (multiple of 16)
   int32_t stage_cap;      // LOG mode: messages staged per tick per instance
+  int32_t stage_u32;      // LOG mode, lines of <= 8 machines: first of the 4 u32 slots that stage a tick's first 8 messages in shared memory
 };
 
 }  // namespace mjp

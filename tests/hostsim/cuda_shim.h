@@ -51,6 +51,7 @@ static inline int __any_sync(unsigned, int pred) { return pred; }
 static inline int __all_sync(unsigned, int pred) { return pred; }
 static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline void __stcs(double2 *p, double2 v) { *p = v; }

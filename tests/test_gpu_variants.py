@@ -297,7 +297,7 @@ def test_rotation_on_device_wide_and_logged(plain, oracle):
     same(plain.run(line, n, seed=5).stats, oracle.run(line, n, seed=5, n_threads=CORES).stats)
     n = 120_000
     line = example_line(run_to=120.0, warm_up=60.0, log=True, up_down=True, max_lines=abi.UINT64_MAX)
-    cap = n * 400
+    cap = n * 1000
     got = plain.run(line, n, seed=9, log_capacity=cap)
     want = oracle.run(line, n, seed=9, log_capacity=cap, n_threads=CORES)
     same(got.stats, want.stats)

@@ -37,7 +37,7 @@ def main():
                ("byte get/set, params", find("auto getb"), find("double r_end[")),
                ("get_end/set_end", find("double r_end["), find("auto px =")),
                ("next_event_time", find("auto next_event_time"), find("// ---- preprocess-model")),
-               ("group minima helpers / rescan_fut", find("const int G = (M + 7) >> 3;"), find("if (fresh_start) {")),
+               ("group minima helpers / rescan_fut", find("constexpr int GSH = sizeof(MaskT)"), find("if (fresh_start) {")),
                ("mark_seen/toggle/type_from", find("auto mark_seen"), find("// ---- SCADA capture")),
                ("job-type draw (whole warp)", find("keep at least one drawn job type"), find("// ---- runables")),
                ("up/down generation (whole warp)", find("Pre-generate the event AFTER"), find("bring-machine-up, then -down")),
