@@ -284,9 +284,13 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       __syncthreads();
     }
   }
-  const uint32_t g = chunk * (uint32_t)nt + tid;             // instances per call < 2^31 (mjp_upload)
+  // SPREAD (p.lane_shift > 0; batches far too small to fill the GPU): only every 2^lane_shift-th lane carries an
+  // instance, so the same instances occupy more warps -- a warp in lock-step costs what its busiest section costs, and
+  // with fewer instances per warp and more warps per scheduler to hide latencies the batch finishes sooner.
+  const uint32_t gt = chunk * (uint32_t)nt + tid;            // instances per call < 2^31 (mjp_upload)
+  const uint32_t g = gt >> p.lane_shift;
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
-  bool active = g < n_inst;
+  bool active = g < n_inst && (gt & ((1u << p.lane_shift) - 1u)) == 0u;
   // A resumed launch continues exactly the instances that were parked at the previous slice boundary.
   const bool resume = SLICE && (rotate ? rot_k > 0 : p.resume != 0);
   const double slice_until = (rotate && rot_k + 1 < (uint32_t)p.rot_slices) ? p.rot_dt * (double)(rot_k + 1) : p.slice_until;
@@ -560,35 +564,16 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
   // load of a tick the cleaning loops below run out of L1; rows beyond a tick's few messages are never
   // touched.  The capture costs no shared memory (same residency as a stats-only run).
   // word: act | m << 8 | n << 16 | job << 32
-  // Lines of up to 8 machines (MT > 0) stage the first SH messages of a tick in SHARED memory, 16 bits each
-  // (act | m << 4 | n << 8): a tick rarely has more, so the flush below reads the scratch in L2 only for the odd
-  // long tick (ncu: the read-back was 3.2 long-scoreboard stalls per issue).  The job number is not stored: jobs
-  // pass a machine in order, so it follows from STARTED(m) at flush time and from whether the machine also started
-  // a job in this tick (flags bits 16-23) -- a machine completes at most one job and starts at most one per tick,
-  // in that order.
-  constexpr int SH = (LOG && MT > 0) ? 8 : 0;
   unsigned long long *g_stage = LOG ? p.stage + (size_t)g * (size_t)p.stage_cap : nullptr;
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
   uint32_t line_cnt = 0;                                   // [:report :line-cnt]
   double aj_ends = 0.0;
-  auto stage16 = [&](int x) -> uint16_t * {                 // message x < SH of the tick
-    return reinterpret_cast<uint16_t *>(&su[(size_t)(p.stage_u32 + (x >> 1)) * nt]) + (x & 1);
-  };
-  auto stage_word = [&](int x) -> unsigned long long {      // the staged message x in the 64-bit form
-    if (x >= SH) return g_stage[x];
-    const unsigned v = *stage16(x), act = v & 15u, m = (v >> 4) & 7u;
-    const bool completes = act == MJP_ACT_BJ || act == MJP_ACT_EJ, starts = act == MJP_ACT_AJ || act == MJP_ACT_SM;
-    const uint32_t job = (completes || starts) ? STARTED(m) - ((completes && ((flags >> (16 + m)) & 1u)) ? 1u : 0u) : 0u;
-    return (unsigned long long)act | ((unsigned long long)m << 8) | ((unsigned long long)(v >> 8) << 16) |
-           ((unsigned long long)job << 32);
-  };
   auto stage_msg = [&](int act, int m, int n, uint32_t job) {      // log/log util/log.clj:30-36
     // print-now? (util/log.clj:220-226) is constant within a tick: a tick before the warm-up or after
     // :max-lines has been reached is never printed, so there is nothing to stage for it
     if (clock < p.warm_up || (uint64_t)line_cnt >= p.max_lines) return;
-    if (n_staged < SH) *stage16(n_staged) = (uint16_t)((unsigned)act | ((unsigned)m << 4) | ((unsigned)n << 8));
-    else if (n_staged < stage_cap)
+    if (n_staged < stage_cap)
       g_stage[n_staged] = (unsigned long long)act | ((unsigned long long)m << 8) |
                           ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);
     else flags |= F_OVF;
@@ -637,7 +622,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
     const bool wide = MT == 0 && MO::popc(seen) > 8;
     bool grouped = !wide;
     for (int x = 0; __any_sync(fm, !wide && x < ns); ++x) if (!wide && x < ns) {
-      const unsigned long long w = stage_word(x);
+      const unsigned long long w = g_stage[x];
       const unsigned act = (unsigned)w & 0xFFu, m = (unsigned)(w >> 8) & 0xFFu, c = log_class(act);
       const MaskT mbit = MJP_BIT(m);
       if (m != pm) { if (gdone & mbit) grouped = false; gdone |= mbit; cdone = 0u; pm = m; pc = 3u; }
@@ -648,7 +633,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       ++q;
     }
     if (!grouped && ns) {
-      for (int x = 0; x < SH && x < ns; ++x) g_stage[x] = stage_word(x);     // the general routine reads the scratch
       const unsigned r = emit_general<MaskT>(lt, g_stage, ns, twoB, twoS, wide ? p.by_rank : nullptr, M);
       q = (int)(r & 0xFFFFu); dropped = (r >> 16) & 0x7FFFu;
       if (r >> 31) flags |= F_OVF;
@@ -724,7 +708,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
     if (on) {
       seen = lead = touched = 0;
       pB = twoB = pS = twoS = 0;
-      flags &= ~(uint32_t)(F_EJ | (SH ? 0x00FF0000u : 0u));
+      flags &= ~(uint32_t)F_EJ;
     }
   };
   // MT == 0: a job whose :ends v has just become known is entered into its group's minimum right away -- nearly
@@ -1022,7 +1006,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
           }
         }
         curjob = id; occ |= 1; STARTED(0) = id;
-        if (SH) flags |= 1u << 16;                           // machine 0 started a job in this tick
         if (K > 1) setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
         p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
         if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
@@ -1138,7 +1121,6 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       if (n - 1 == 0) empty |= bit;
       full &= ~bbit;
       occ |= bit; STARTED(i) = id;
-      if (SH) flags |= 1u << (16 + i);
       if (fired & bit) { dup |= bit; up ^= bit; }
     }
     if (MT > 0) {                                            // record-actions core.clj:304-326, in the order

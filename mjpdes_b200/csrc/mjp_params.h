@@ -39,6 +39,8 @@ struct KParams {
   int32_t resume;         // 1: continue the instances parked by the previous launch
   int32_t park_words;     // rows of `park`
   uint32_t *park;         // [park_words][n_inst] parked per-instance state
+  int32_t lane_shift;     // spread: instance g runs on lane g << lane_shift of the grid (0 = every lane carries one)
+  int32_t pad0;
   // rotation (see mjp_line_kernel.cuh): resident CTAs pull (chunk, slice) items; 0 slices = off
   int32_t rot_slices;     // slices of sim time the run is cut into
   uint32_t rot_chunks;    // chunks of blockDim instances
@@ -57,7 +59,6 @@ struct KParams {
   int32_t nf64, nu32;     // per-thread slots
   int32_t const_bytes;    // CTA constant table size (multiple of 16)
   int32_t stage_cap;      // LOG mode: messages staged per tick per instance
-  int32_t stage_u32;      // LOG mode, lines of <= 8 machines: first of the 4 u32 slots that stage a tick's first 8 messages in shared memory
 };
 
 }  // namespace mjp

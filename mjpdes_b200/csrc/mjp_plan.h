@@ -69,8 +69,8 @@ inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 //   cold f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1] (+ ENDS[M] when M > 32 and the layout is cold)         cold u32: FUT_N[M] STARTED[M] JT[R/4] EIDX[M] if REPLAY
 //   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] GE[G] GU[G] unless :ends are in registers (G = ceil(M/GS) groups, GS = 4 up to 32 machines, 8 beyond)
 //   hot  u32: CNT[M-1]
-// SCADA capture (LOG) stages a tick's messages in a global scratch of stage_cap words per instance; lines of up to 8
-// machines keep the first 8 of them here instead (4 u32 slots, 16 bits per message).
+// SCADA capture (LOG) stages a tick's messages in a global scratch of stage_cap words per instance, not here
+// (staging in shared memory was measured twice and lost both times, profiles/README.md).
 // Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX);
 // with it they live in a global scratch of cold_f64_slots / cold_u32_slots rows per instance.
 inline int cold_f64_slots(const KParams &kp) { return 5 * kp.M - 1; }
@@ -81,12 +81,11 @@ inline int cold_u32_slots(const KParams &kp, bool replay) {
 }
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
-  kp.stage_u32 = -1;
+  (void)log;
   const int groups = M > 32 ? (M + 7) / 8 : (M + 3) / 4;          // GS = 8 with 64-bit masks, 4 otherwise
   const int ends_hot = (cold && cold_ends_slots(kp)) ? 0 : M;
   kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : ends_hot + 2 * groups);
   kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1);
-  if (log && ends_in_regs) { kp.stage_u32 = kp.nu32; kp.nu32 += 4; }     // SCADA: 8 x 16-bit messages of the current tick
   return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
 }
 

@@ -19,6 +19,8 @@ def main():
     hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
     hdr = rows[hi]
     ie, te, sm = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
+    ni = hdr.index("stall_no_inst") if "stall_no_inst" in hdr else None
+    lsb = hdr.index("stall_long_sb") if "stall_long_sb" in hdr else None
     inst = [r for r in rows[hi + 1:] if len(r) > te]
     lm = N.line_map(SO, mangled)
     assert len(lm) == len(inst), (len(lm), len(inst), "rebuild mismatch: profile and .so differ")
@@ -56,13 +58,16 @@ def main():
                 for name, a in marks:
                     if l >= a:
                         key = name
-        x = agg.setdefault(key, [0, 0, 0])
+        x = agg.setdefault(key, [0, 0, 0, 0, 0])
         x[0] += int(r[ie] or 0); x[1] += int(r[te] or 0); x[2] += int(r[sm] or 0)
+        if ni is not None: x[3] += int(r[ni] or 0)
+        if lsb is not None: x[4] += int(r[lsb] or 0)
     ti = sum(v[0] for v in agg.values())
     ts = sum(v[2] for v in agg.values())
-    print(f"{'section':40s} {'% warp-inst':>11s} {'lanes':>6s} {'% samples':>9s}" + (f" {'inst/event':>10s}" if events else ""))
+    print(f"{'section':40s} {'% warp-inst':>11s} {'lanes':>6s} {'% samples':>9s} {'no_inst':>8s} {'long_sb':>8s}" + (f" {'inst/event':>10s}" if events else ""))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        print(f"{k:40s} {100 * v[0] / ti:10.1f}% {v[1] / max(v[0], 1):6.1f} {100 * v[2] / max(ts, 1):8.1f}%" + (f" {v[0] / events:10.2f}" if events else ""))
+        print(f"{k:40s} {100 * v[0] / ti:10.1f}% {v[1] / max(v[0], 1):6.1f} {100 * v[2] / max(ts, 1):8.1f}% {100 * v[3] / max(ts, 1):7.1f}% {100 * v[4] / max(ts, 1):7.1f}%"
+              + (f" {v[0] / events:10.2f}" if events else ""))
 
 if __name__ == "__main__":
     main()

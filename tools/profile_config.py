@@ -18,6 +18,7 @@ from mjpdes_b200 import abi, engine, workloads as wl
 CONFIGS = {
     # name: (line factory(n), n, log records per instance, sliced quantum (q0, q1) or None)
     "C2_example": (lambda n: wl.example_line(warm_up=200.0, run_to=2000.0), 104192, 0, None),
+    "C2_small": (lambda n: wl.example_line(warm_up=500.0, run_to=5000.0), 10000, 0, None),
     "C2_example_full": (lambda n: wl.example_line(), 100000, 0, None),
     "C3_sweep10": (lambda n: wl.sweep10_line(n, warm_up=100.0, run_to=1000.0, first=0), 104192, 0, None),
     "C4_mixed20_stats": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=1000.0, log=False), 10000, 0, None),
