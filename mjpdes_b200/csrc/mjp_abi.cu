@@ -455,22 +455,6 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     // sim time, and the resident CTAs pull (chunk, slice) items from a queue (mjp_line_kernel.cuh): all instances
     // of a batch take about the same time, so otherwise the last, partly filled wave would cost a full pass.
     kp.rot_slices = 0;
-    kp.lane_shift = 0;
-    {
-      // Spread: a batch that would leave most of the GPU empty puts its instances on every 2nd / 4th / 8th lane, i.e.
-      // into 2-8 times as many warps (mjp_line_kernel.cuh).  Chosen so that the grid still fits the resident capacity.
-      static const char *spread_env = std::getenv("MJP_SPREAD");          // A/B measurements: 0 = never, 1-3 = forced shift
-      const bool sl = resume || until < std::numeric_limits<double>::infinity();
-      int occ = 0;
-      cudaError_t oe = launch_line_kernel(replay, hash, sl, h->want_log, cold, kp, 0, threads, h->smem_bytes, h->stream, &occ);
-      const long long lanes = (oe == cudaSuccess) ? (long long)occ * (long long)sms * threads : 0;
-      int shift = 0;
-      while (shift < 3 && lanes > 0 && ((long long)kp.n_inst << (shift + 1)) <= lanes / 2) ++shift;
-      if (spread_env) shift = spread_env[0] >= '0' && spread_env[0] <= '3' ? spread_env[0] - '0' : shift;
-      kp.lane_shift = shift;                                               // (the park is laid out per instance, not per lane)
-      blocks = (int)((((unsigned long long)kp.n_inst << shift) + threads - 1) / threads);
-      cudaGetLastError();
-    }
     static const char *rot_env = std::getenv("MJP_ROTATE");               // A/B measurements: 0 = never
     static const char *rot_slices_env = std::getenv("MJP_ROTATE_SLICES");
     if (!resume && until == std::numeric_limits<double>::infinity() && std::isfinite(kp.run_to) &&

@@ -284,13 +284,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       __syncthreads();
     }
   }
-  // SPREAD (p.lane_shift > 0; batches far too small to fill the GPU): only every 2^lane_shift-th lane carries an
-  // instance, so the same instances occupy more warps -- a warp in lock-step costs what its busiest section costs, and
-  // with fewer instances per warp and more warps per scheduler to hide latencies the batch finishes sooner.
-  const uint32_t gt = chunk * (uint32_t)nt + tid;            // instances per call < 2^31 (mjp_upload)
-  const uint32_t g = gt >> p.lane_shift;
+  const uint32_t g = chunk * (uint32_t)nt + tid;             // instances per call < 2^31 (mjp_upload)
   // Lanes past the end of the batch stay in the warp (the loop below runs in lock-step) but do nothing.
-  bool active = g < n_inst && (gt & ((1u << p.lane_shift) - 1u)) == 0u;
+  bool active = g < n_inst;
   // A resumed launch continues exactly the instances that were parked at the previous slice boundary.
   const bool resume = SLICE && (rotate ? rot_k > 0 : p.resume != 0);
   const double slice_until = (rotate && rot_k + 1 < (uint32_t)p.rot_slices) ? p.rot_dt * (double)(rot_k + 1) : p.slice_until;

@@ -39,8 +39,6 @@ struct KParams {
   int32_t resume;         // 1: continue the instances parked by the previous launch
   int32_t park_words;     // rows of `park`
   uint32_t *park;         // [park_words][n_inst] parked per-instance state
-  int32_t lane_shift;     // spread: instance g runs on lane g << lane_shift of the grid (0 = every lane carries one)
-  int32_t pad0;
   // rotation (see mjp_line_kernel.cuh): resident CTAs pull (chunk, slice) items; 0 slices = off
   int32_t rot_slices;     // slices of sim time the run is cut into
   uint32_t rot_chunks;    // chunks of blockDim instances

@@ -25,14 +25,6 @@ prof() {   # name
   cat $O/${TAG}_$1_events.json; echo
   timeout 900 $NCU -f -o $O/${TAG}_$1 python tools/profile_config.py $1 > $O/${TAG}_$1_ncu.log 2>&1; echo "ncu $1 exit $?"
 }
-if has ab_spread; then
-  for c in C4_mixed20_stats C4_mixed20_scada C2_small; do
-    for v in 0 1 2 3; do
-      echo -n "spread=$v $c: "; MJP_SPREAD=$v timeout 600 python tools/profile_config.py $c 2>&1 | tail -1
-    done
-  done > $O/${TAG}_ab_spread.log 2>&1
-  cut -c1-160 $O/${TAG}_ab_spread.log
-fi
 if has ab_persist; then
   for c in C3_sweep10 C4_mixed20_stats_many C5_long50 C5_long50_slice C4_mixed20_scada example_scada; do
     for v in 0 1; do
