@@ -1003,7 +1003,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
         }
         curjob = id; occ |= 1; STARTED(0) = id;
         if (K > 1) setb(s_jt, cs, (int)(id & Rm), (uint32_t)type);
-        p.enters[(size_t)(id & Rm) * n_inst + g] = clock;
+        p.enters[(size_t)g * (Rm + 1u) + (id & Rm)] = clock;
         if (fired & 1) { dup |= 1; up ^= 1; }              // machine-future core.clj:194-198
       }
     }
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
         if (n + 1 == (int)(cw >> 24)) full |= bit;
         empty &= ~(bit << 1);
       } else {
-        const double ent = p.enters[(size_t)(id & Rm) * n_inst + g];
+        const double ent = p.enters[(size_t)g * (Rm + 1u) + (id & Rm)];
         if (HASH) { hmix(h, (uint64_t)MJP_ACT_EJ | ((uint64_t)i << 8) | ((uint64_t)id << 32)); hmix(h, d2bits(clock)); hmix(h, d2bits(ent)); hmix(h, d2bits(get_end(i))); }
         mark_seen(i);
         if (LOG) stage_msg(MJP_ACT_EJ, i, 0, id);

@@ -31,7 +31,8 @@ struct KParams {
   int64_t *njobs; double *residence; double *blocked, *starved, *occ; double *final_clock;
   int64_t *curjob; uint64_t *n_events; uint64_t *hash; uint8_t *status;
   // scratch
-  double *enters;         // [R][n_inst] :enters of the jobs in the line
+  double *enters;         // [n_inst][R] :enters of the jobs in the line: a ring per instance, so that the 4 consecutive jobs
+                          // of one 32-byte sector are written and read back while the sector is still in the L2
   double *cold_f;         // COLD variants: [5M-1][n_inst]  FUT_T NXT_T BS SS LASTCLK
   uint32_t *cold_u;       // COLD variants: [2M + R/4 + M][n_inst]  FUT_N STARTED JT EIDX
   // time slicing
