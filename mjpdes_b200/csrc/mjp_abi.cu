@@ -406,10 +406,14 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     // else fits, COLD and/or 32-thread CTAs are the fallback.
     static const char *cold_env = std::getenv("MJP_COLD");            // A/B measurements: 0 = never, 1 = always
     const size_t sms = (size_t)(h->sm_count > 0 ? h->sm_count : 148);
+    kp.started_hot = 0;
+    static const char *ec_env = std::getenv("MJP_ENDS_COLD");             // A/B measurements: 0 / 1 force it
+    kp.ends_cold = ec_env ? (ec_env[0] == '1') : (kp.M > 32);
     auto cta_bytes = [&](bool c, int t) {
       mjp::KParams tmp = kp;
       const bool mt_ = !c && use_register_ends(kp, h->want_log, t);
-      return (size_t)kp.const_bytes + mjp::plan_layout(tmp, mt_, replay, h->want_log, c) * t;
+      const size_t per_thread_ = mjp::plan_layout(tmp, mt_, replay, h->want_log, c);       // (sets tmp.const_bytes too)
+      return (size_t)tmp.const_bytes + per_thread_ * t;
     };
     auto fits = [&](bool c, int t) { return cta_bytes(c, t) <= h->smem_optin; };
     int threads = 0;
@@ -425,6 +429,18 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     else if (fits(true, 32)) { threads = 32; cold = true; }
     else return fail(h, MJP_ERR_UNSUPPORTED, "line state does not fit in shared memory (M, sum N too large)");
     h->block_threads = threads;
+    if (cold) {
+      // STARTED[M] (read by every job movement) stays in shared memory when that costs no CTA per SM: the kernels run
+      // at most 12 (32-bit masks) / 8 (64-bit masks) CTAs per SM for their registers
+      const size_t reg_limit = kp.M > 32 ? 8 : 12;
+      const size_t without = std::min(reg_limit, h->smem_optin / (cta_bytes(true, threads) + 1024));
+      mjp::KParams tmp = kp;
+      tmp.started_hot = 1;
+      const size_t with_thread = mjp::plan_layout(tmp, false, replay, h->want_log, true);
+      const size_t with_bytes = (size_t)tmp.const_bytes + with_thread * threads;
+      const size_t with = std::min(reg_limit, h->smem_optin / (with_bytes + 1024));
+      kp.started_hot = (with >= without && with_bytes <= h->smem_optin) ? 1 : 0;
+    }
     {
       // the park layout follows from the variant: a resume must be the same kind of launch on the same substreams
       mjp_handle::ParkKey key;

@@ -311,15 +311,21 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
 #define EJENT      sf[(hb + 1) * nt]            /* :ent of this tick's :ej            */
 #define TMINUD     sf[(hb + 2) * nt]            /* earliest pending up/down time (cache) */
   // :ends (MT == 0): with the per-group minima below it is read only when a group is re-scanned, so the widest
-  // lines (64-bit masks) keep it in the cold scratch too -- it was over half of their shared memory (M = 50:
-  // 732 -> 332 bytes per instance, 4 -> 7 CTAs per SM)
-  constexpr bool ENDS_COLD = COLD && sizeof(MaskT) == 8;
-  const int hg = hb + 3 + (ENDS_COLD ? 0 : M);             // first group-minimum slot
-#define ENDS_S(i)  (*(ENDS_COLD ? &cfp[(5 * M - 1 + (i)) * cs] : &sf[(hb + 3 + (i)) * nt]))   /* :status :ends, or remaining work (MT == 0 only) */
+  // lines keep it in the cold scratch too when that buys CTAs per SM -- it was over half of their shared memory
+  const bool ends_cold = COLD && p.ends_cold != 0;         // decided by the host: when it buys CTAs per SM
+  const int hg = hb + 3 + (ends_cold ? 0 : M);             // first group-minimum slot
+  double *const ends_base = ends_cold ? cfp + (size_t)(5 * M - 1) * cs : sf + (size_t)(hb + 3) * nt;
+  const uint32_t ends_stride = ends_cold ? (uint32_t)cs : (uint32_t)nt;
+#define ENDS_S(i)  ends_base[(size_t)(i) * ends_stride]   /* :status :ends, or remaining work (MT == 0 only) */
 #define GMINE(gr)  sf[(hg + (gr)) * nt]          /* MT == 0: min :ends over the tracked machines of group gr   */
 #define GMINU(gr)  sf[(hg + G + (gr)) * nt]      /* MT == 0: min pending up/down time over group gr            */
 #define FUT_N(i)   cup[(i) * cs]                 /* :future index                      */
-#define STARTED(i) cup[(M + (i)) * cs]           /* jobs started on machine i          */
+  // jobs started on machine i: read by every job movement, so a cold layout keeps it in shared memory after the
+  // buffer counts whenever the M extra words per instance cost no CTA per SM (p.started_hot, decided by the host)
+  const bool started_hot = COLD && p.started_hot != 0;
+  uint32_t *const st_base = started_hot ? su + (size_t)(hu + M - 1) * nt : cup + (size_t)M * cs;
+  const uint32_t st_stride = started_hot ? (uint32_t)nt : (uint32_t)cs;       // (instances per call < 2^31)
+#define STARTED(i) st_base[(size_t)(i) * st_stride]
 #define CNT(b)     su[(hu + (b)) * nt]          /* bits 0-7 (count :holding) of buffer b; bits 8-18 this tick's
                                                    occupancy bookkeeping, see buffer_tick_bits; bits 24-31 :N */
   uint32_t *s_jt = cup + (size_t)(COLD ? 2 * M : 3 * M - 1) * cs;  /* job type ring, 4 per word    */
@@ -438,9 +444,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
   // machines that own an :ends candidate, and the earliest pending up/down time -- are kept per GROUP of GS
   // machines (GMINE / GMINU) and maintained incrementally, so that no pass over all M machines is left on the
   // per-micro-step path: a group is re-read only when its minimum is consumed or a member leaves it.
-  // Group size GS: 4 machines up to 32 machines, 8 beyond (at most 8 groups either way): a rescan reads GS values
-  // at a few active lanes, the per-micro-step min reads G values at all lanes -- about sqrt(M) each is the balance.
-  constexpr int GSH = sizeof(MaskT) == 4 ? 2 : 3, GS = 1 << GSH;
+  // Group size GS = 4 (at most 16 groups): a rescan reads GS values at a few active lanes, the per-micro-step min reads
+  // G values at all lanes.  Measured on 10, 20 and 50 machines: groups of 4 beat groups of 8 (by 11 % on 50 machines)
+  // and groups of 2 (which cost the 20-machine line a CTA per SM).
+  constexpr int GSH = 2, GS = 1 << GSH;
   constexpr uint32_t GSM = (1u << GS) - 1u;
   const int G = (M + GS - 1) >> GSH;
   auto grp_bits = [&](MaskT m, int gr) -> uint32_t { return (uint32_t)(m >> (GS * gr)) & GSM; };
@@ -471,7 +478,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
         double acc = INF;
         for (int i = GS * gr; i < GS * gr + GS && i < M; ++i) { const double t = FUT_T(i); acc = t < acc ? t : acc; }
         GMINU(gr) = acc; GMINE(gr) = INF;
-        t0 = acc < t0 ? acc : t0;
+        if (acc < t0) { t0 = acc; m_udc = 0; }
+        if (acc == t0) m_udc |= MJP_BIT(gr);               // MT == 0: m_udc = the GROUPS that attain the minimum
       }
       TMINUD = t0;
     }
@@ -888,13 +896,17 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
         tmin = e < tmin ? e : tmin;
       }
     }
-    bool live2 = live;
-    if (live && (now_any ? (tmin < clock) : (tmin == INF))) {
-      finish(now_any ? MJP_INST_CLOCK_BACK : MJP_INST_NO_RUNABLES);                           // core.clj:133,739
-      live2 = false;
+    // (the paths that end an instance sit behind a vote each: as predicated code their operands cost ~17 issued
+    // instructions per micro-step, ncu)
+    const bool stuck = live && (now_any ? (tmin < clock) : (tmin == INF));
+    if (__any_sync(am, stuck)) {
+      if (stuck) {
+        finish(now_any ? MJP_INST_CLOCK_BACK : MJP_INST_NO_RUNABLES);                         // core.clj:133,739
+        live = false;
+      }
     }
-    live = live2;
-    if (live && now_any && c_aj != 0 && next_type() < 0) {
+    const bool no_type = live && now_any && c_aj != 0 && next_type() < 0;
+    if (__any_sync(am, no_type)) if (no_type) {
       // add-job (a "now" candidate, first action of its batch) has no job type to draw: the reference dies in
       // it before logging anything -- the previous tick is never pushed, nothing of this batch is executed
       finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED : MJP_INST_JOBTYPE_NIL); live = false;
@@ -928,8 +940,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       late |= m_f;                                            // (every use of the pre-advance `late` is above)
       // same for the up/down times: members of the groups at t* that fire, new group minimum over the others
       // (the fired machines add their next event time below)
-      uint32_t uq = 0;
-      if (live && tmin_ud == tstar) for (int gr = 0; gr < G; ++gr) if (GMINU(gr) == tstar) uq |= 1u << gr;
+      uint32_t uq = (live && tmin_ud == tstar) ? (uint32_t)m_udc : 0u;
       for (; __any_sync(am, uq != 0);) if (uq) {
         const int gr = __ffs((int)uq) - 1; uq &= uq - 1;
         const uint32_t is_dup = grp_bits(dup, gr);
@@ -962,8 +973,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       flush_tick(do_flush);
       if (will_log && !(flags & F_TICK)) { TICKCLK = clock; flags |= F_TICK; }
     }
-    n_ev += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
-                MO::popc(b_us) + MO::popc(b_bl) + MO::popc(b_ub);
+    if (MT > 0)                                               // M <= 8: two packed words instead of eight counts
+      n_ev += __popc((uint32_t)b_st | ((uint32_t)b_us << 8) | ((uint32_t)b_bl << 16) | ((uint32_t)b_ub << 24)) +
+              __popc((uint32_t)b_aj | ((uint32_t)b_tb << 8) | ((uint32_t)b_tm << 16) | ((uint32_t)b_ud << 24));
+    else
+      n_ev += MO::popc(b_aj) + MO::popc(b_ud) + MO::popc(b_tb) + MO::popc(b_tm) + MO::popc(b_st) +
+              MO::popc(b_us) + MO::popc(b_bl) + MO::popc(b_ub);
 
     // ---- run the batch in generator order, core.clj:742 ----
     if (__any_sync(am, b_aj != 0)) {
@@ -1072,7 +1087,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       if (MT == 0 && __any_sync(am, (b_ud & ~dup_before) != 0)) {
         if (b_ud & ~dup_before) {                            // an event fired: the earliest pending up/down time anew
           double t0 = INF;
-          for (int gr = 0; gr < G; ++gr) { const double v = GMINU(gr); t0 = v < t0 ? v : t0; }
+          for (int gr = 0; gr < G; ++gr) {
+            const double v = GMINU(gr);
+            if (v < t0) { t0 = v; m_udc = 0; }
+            if (v == t0) m_udc |= MJP_BIT(gr);
+          }
           TMINUD = t0;
         }
       }
@@ -1150,7 +1169,8 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
         else { B ^= bit; toggle(pB, twoB, bit); }
       }
     }
-    if (live && ((flags & (F_TAPE | F_OVF)) != 0 || seen == 0)) {        // rare: one test on the common path
+    const bool broken = live && ((flags & (F_TAPE | F_OVF)) != 0 || seen == 0);
+    if (__any_sync(am, broken)) if (broken) {                             // rare: one vote on the common path
       finish((flags & F_TAPE) ? MJP_INST_TAPE_EXHAUSTED
                               : ((flags & F_OVF) ? MJP_INST_TICK_OVERFLOW
                                                  : MJP_INST_LOGBUF_EMPTY));   // push-log returned nil, util/log.clj:95

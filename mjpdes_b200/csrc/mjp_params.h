@@ -55,6 +55,8 @@ struct KParams {
   unsigned long long *log_cursor;   // [0] next free record, [1] records dropped
   unsigned long long *stage;        // LOG mode: [n_inst][stage_cap] messages of the current tick (global scratch)
   // shared-memory layout
+  int32_t started_hot;    // cold layouts: STARTED[M] lives in shared memory after CNT (1) or in the cold scratch (0)
+  int32_t ends_cold;      // cold layouts: ENDS[M] lives in the cold scratch (rows 5M-1 .. 6M-2) instead of shared memory
   int32_t nf64, nu32;     // per-thread slots
   int32_t const_bytes;    // CTA constant table size (multiple of 16)
   int32_t stage_cap;      // LOG mode: messages staged per tick per instance

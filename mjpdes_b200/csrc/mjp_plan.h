@@ -67,25 +67,26 @@ inline size_t plan_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Per-thread shared-memory slots of one kernel variant (must mirror the macros in mjp_line_kernel.cuh):
 //   cold f64: FUT_T[M] NXT_T[M] BS[M] SS[M] LASTCLK[M-1] (+ ENDS[M] when M > 32 and the layout is cold)         cold u32: FUT_N[M] STARTED[M] JT[R/4] EIDX[M] if REPLAY
-//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] GE[G] GU[G] unless :ends are in registers (G = ceil(M/GS) groups, GS = 4 up to 32 machines, 8 beyond)
-//   hot  u32: CNT[M-1]
+//   hot  f64: TICKCLK EJENT TMINUD | ENDS[M] GE[G] GU[G] unless :ends are in registers (G = ceil(M/4) groups)
+//   hot  u32: CNT[M-1] (+ STARTED[M] in a cold layout when kp.started_hot: set by the caller BEFORE plan_layout when the
+//             extra words cost no CTA per SM)
 // SCADA capture (LOG) stages a tick's messages in a global scratch of stage_cap words per instance, not here
 // (staging in shared memory was measured twice and lost both times, profiles/README.md).
 // Without `cold` the cold slots precede the hot ones in the same shared arrays (u32: FUT_N STARTED CNT JT EIDX);
 // with it they live in a global scratch of cold_f64_slots / cold_u32_slots rows per instance.
 inline int cold_f64_slots(const KParams &kp) { return 5 * kp.M - 1; }
 // lines of more than 32 machines keep :ends in the cold scratch as well (rows 5M-1 .. 6M-2), see mjp_line_kernel.cuh
-inline int cold_ends_slots(const KParams &kp) { return kp.M > 32 ? kp.M : 0; }
+inline int cold_ends_slots(const KParams &kp) { return kp.M; }      // (allocated for every cold layout; used when kp.ends_cold)
 inline int cold_u32_slots(const KParams &kp, bool replay) {
   return 2 * kp.M + (kp.K > 1 ? (kp.R >> 2) : 0) + (replay ? kp.M : 0);      // no job-type ring for a single type
 }
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
   (void)log;
-  const int groups = M > 32 ? (M + 7) / 8 : (M + 3) / 4;          // GS = 8 with 64-bit masks, 4 otherwise
-  const int ends_hot = (cold && cold_ends_slots(kp)) ? 0 : M;
+  const int groups = (M + 3) / 4;                                  // GS = 4
+  const int ends_hot = (cold && kp.ends_cold) ? 0 : M;
   kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : ends_hot + 2 * groups);
-  kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1);
+  kp.nu32 = (cold ? 0 : cold_u32_slots(kp, replay)) + (M - 1) + ((cold && kp.started_hot) ? M : 0);
   return (size_t)kp.nf64 * 8 + (size_t)kp.nu32 * 4;
 }
 

@@ -42,12 +42,15 @@ def lib():
 
 
 def run(line, n_inst, mode=abi.RNG_COUNTER, seed=0, first_instance_id=0, want_hash=True, log_capacity=0, cold=False,
-        slices=(), tapes=None, rotation=0):
+        slices=(), tapes=None, rotation=0, started_hot=None):
     stats = abi.HostStats(line, n_inst)
     d, r, s = line.desc(), abi.RngSpec(mode, 0, seed, first_instance_id), stats.struct()
     hlog = abi.HostLog(log_capacity) if log_capacity else None
     sl = np.ascontiguousarray(slices, np.float64)
     lib().hostsim_set_rotation(int(rotation))
+    # cold layouts: STARTED[M] in shared memory or in the scratch; by default alternate with the batch size so that
+    # every caller (the fuzzers included) exercises both
+    lib().hostsim_set_started_hot(int((n_inst & 1) if started_hot is None else started_hot))
     rc = lib().hostsim_run_sliced(C.byref(d), n_inst, C.byref(r), C.byref(s), int(want_hash),
                                   C.byref(hlog.struct()) if hlog else None, int(cold),
                                   abi.ptr(sl, C.c_double) if len(sl) else None, len(sl),

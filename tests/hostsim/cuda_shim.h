@@ -25,6 +25,7 @@ namespace mjp {
 alignas(16) unsigned char smem_raw[1 << 20];
 alignas(16) double red[4096];
 }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline void __syncthreads() {}
 static inline void __threadfence() {}
 static inline unsigned atomicAdd(unsigned *a, unsigned v) { unsigned o = *a; *a = o + v; return o; }

@@ -12,6 +12,10 @@
 static int g_rot_slices = 0;
 extern "C" void hostsim_set_rotation(int slices) { g_rot_slices = slices; }
 
+// cold layouts: keep STARTED[M] in "shared memory" (what the host does when it costs no CTA per SM)
+static int g_started_hot = 0;
+extern "C" void hostsim_set_started_hot(int on) { g_started_hot = on; }
+
 // One launch per slice boundary in `slices` (then one to the end), resuming the parked state each time.
 extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng, mjp_stats_out *s,
                                   int want_hash, mjp_log_out *log, int force_cold, const double *slices, int n_slices,
@@ -46,6 +50,8 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   for (size_t q = 0; q < n_inst; ++q) { s->njobs[q] = 0; s->residence_sum[q] = 0; s->n_events[q] = 0; }
   const bool cold = force_cold != 0;
   const bool mt_ok = !cold && M >= 2 && M <= 8;
+  kp.started_hot = (cold && g_started_hot) ? 1 : 0;
+  kp.ends_cold = (cold && (M > 32 || g_started_hot)) ? 1 : 0;           // both placements get exercised
   mjp::plan_layout(kp, mt_ok, rng->mode != MJP_RNG_COUNTER, want_log_early, cold);
   std::vector<double> coldf((size_t)(mjp::cold_f64_slots(kp) + mjp::cold_ends_slots(kp)) * n_inst);
   std::vector<uint32_t> coldu((size_t)mjp::cold_u32_slots(kp, true) * n_inst);

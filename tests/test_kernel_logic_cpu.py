@@ -96,7 +96,9 @@ def test_cold_state_layout(oracle, trial):
     M = [3, 10, 20, 33, 50, 64][trial]
     line = random_line(rng, M, int(rng.integers(1, 5)), run_to=150.0, warm_up=15.0, up_down=bool(trial % 2))
     mode = MODES[trial % 2]
-    assert_same(H.run(line, 3, mode=mode, seed=trial, cold=True), oracle.run(line, 3, mode=mode, seed=trial).stats)
+    want = oracle.run(line, 3, mode=mode, seed=trial).stats
+    for started_hot in (False, True):            # STARTED[M] in the scratch / in shared memory (host's choice, mjp_abi.cu)
+        assert_same(H.run(line, 3, mode=mode, seed=trial, cold=True, started_hot=started_hot), want)
 
 
 def test_cold_state_layout_with_scada_log(oracle):
