@@ -40,7 +40,7 @@ if has cliff; then
 fi
 if has ncu_c2; then prof C2_example; fi
 if has ncu_wide; then prof C3_sweep10; prof C4_mixed20_stats_many; prof C5_long50; fi
-if has ncu_c4; then prof C4_mixed20_stats; fi
+if has ncu_c4; then prof C4_mixed20_stats; prof C4_mixed20_scada; prof C4_mixed20_scada_many; fi
 if has ncu_slice; then prof C5_long50_slice; fi
 if has ncu_c4s; then prof C4_mixed20_stats_many; fi
 if has ncu_scada; then prof C4_mixed20_scada_many; prof example_scada; fi

@@ -23,8 +23,8 @@ CONFIGS = {
     "C3_sweep10": (lambda n: wl.sweep10_line(n, warm_up=100.0, run_to=1000.0, first=0), 104192, 0, None),
     "C4_mixed20_stats": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=1000.0, log=False), 10000, 0, None),
     "C4_mixed20_stats_many": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=600.0, log=False), 75776, 0, None),
-    "C4_mixed20_scada": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=400.0), 10000, 14000, None),
-    "C4_mixed20_scada_many": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=250.0), 75776, 6000, None),
+    "C4_mixed20_scada": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=700.0), 10000, 22000, None),
+    "C4_mixed20_scada_many": (lambda n: wl.mixed20_line(warm_up=100.0, run_to=400.0), 75776, 11000, None),
     "example_scada": (lambda n: wl.example_line(warm_up=100.0, run_to=400.0, log=True, up_down=True,
                                                 max_lines=abi.UINT64_MAX), 104192, 4000, None),
     "C5_long50_slice": (lambda n: wl.long50_line(warm_up=1e5, run_to=1e6), 75776, 0, (20.0, 120.0)),
