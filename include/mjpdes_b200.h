@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MJP_ABI_VERSION 2
+#define MJP_ABI_VERSION 3
 
 /* ---- call status ------------------------------------------------------- */
 enum {
@@ -197,7 +197,10 @@ typedef struct mjp_log_record {
   uint32_t job;       /* :j (aj, bj, ej, sm), else 0                           */
   uint32_t instance;  /* index within this call                                */
   uint32_t line;      /* :line                                                 */
-  uint16_t n;         /* :n for bj/sm (count BEFORE the move); job-type index for aj */
+  uint8_t  n;         /* :n for bj/sm (count BEFORE the move); job-type index for aj */
+  uint8_t  ord;       /* position of the message in :log-buf, i.e. in the tick's EXECUTION order
+                         (mod 256): clean-log-buf regroups a tick by machine, and the :dets
+                         snapshots (util/log.clj:11-28) depend on the order the moves were made in */
   uint8_t  act;       /* MJP_ACT_*                                             */
   uint8_t  machine;   /* :m (topology index); :bf is machine-1 for sm, machine for bj */
 } mjp_log_record;
@@ -207,6 +210,13 @@ typedef struct mjp_log_out {
   uint64_t capacity;         /* in records                                      */
   uint64_t count;            /* OUT: records written (<= capacity)              */
   uint64_t dropped;          /* OUT: records that did not fit                   */
+  /* Optional (may be NULL): [n_inst][2 M], where the jobs were at the END of the clock tick whose records are
+   * the instance's first -- what (log/detail model) (util/log.clj:11-28) needs to start from, since nothing before
+   * the warm-up is in the record stream (undo that tick's moves in reverse `ord` order to get the state before it).
+   * Word i: number of the last job started on machine i (0 = none yet); word M+i: bit 0 = machine i holds a job,
+   * bits 8-15 = (count :holding) of buffer i.  Jobs pass through a serial line in order, so machine i holds job
+   * started[i] and buffer i holds started[i+1]+1 .. started[i+1]+count.  0xFFFFFFFF everywhere: nothing printed yet. */
+  uint32_t *first_state;
 } mjp_log_out;
 
 /* ---- handle ---------------------------------------------------------------- */

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # call status
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, LOG_TRUNCATED = range(6)
@@ -97,17 +97,17 @@ class StatsOut(C.Structure):
 
 class LogRecord(C.Structure):
     _fields_ = [("clk", C.c_double), ("aux", C.c_double), ("job", C.c_uint32), ("instance", C.c_uint32),
-                ("line", C.c_uint32), ("n", C.c_uint16), ("act", C.c_uint8), ("machine", C.c_uint8)]
+                ("line", C.c_uint32), ("n", C.c_uint8), ("ord", C.c_uint8), ("act", C.c_uint8), ("machine", C.c_uint8)]
 
 
 LOG_RECORD_DTYPE = np.dtype([("clk", "<f8"), ("aux", "<f8"), ("job", "<u4"), ("instance", "<u4"),
-                             ("line", "<u4"), ("n", "<u2"), ("act", "u1"), ("machine", "u1")])
+                             ("line", "<u4"), ("n", "u1"), ("ord", "u1"), ("act", "u1"), ("machine", "u1")])
 assert LOG_RECORD_DTYPE.itemsize == 32 and C.sizeof(LogRecord) == 32
 
 
 class LogOut(C.Structure):
     _fields_ = [("records", C.POINTER(LogRecord)), ("capacity", C.c_uint64), ("count", C.c_uint64),
-                ("dropped", C.c_uint64)]
+                ("dropped", C.c_uint64), ("first_state", C.POINTER(C.c_uint32))]
 
 
 class Config(C.Structure):
@@ -222,11 +222,18 @@ class HostStats:
 
 
 class HostLog:
-    def __init__(self, capacity: int):
+    """Caller buffers of mjp_log_out.  ``n_inst`` and ``M`` given: also ``first_state`` [n_inst][2M], where the jobs
+    were at each instance's first printed message (what the :dets snapshots start from, scada.DetsTracker)."""
+
+    def __init__(self, capacity: int, n_inst: int = 0, M: int = 0):
         self.records = np.zeros(int(capacity), LOG_RECORD_DTYPE)
         self._s = LogOut()
         self._s.records = C.cast(self.records.ctypes.data, C.POINTER(LogRecord))
         self._s.capacity = int(capacity)
+        self.first_state = None
+        if n_inst and M:
+            self.first_state = np.full((int(n_inst), 2 * int(M)), 0xFFFFFFFF, np.uint32)
+            self._s.first_state = C.cast(self.first_state.ctypes.data, C.POINTER(C.c_uint32))
 
     def struct(self) -> LogOut:
         return self._s
@@ -258,7 +265,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    p = path or LIB_PATH
+    p = path or os.environ.get("MJP_LIB") or LIB_PATH      # MJP_LIB: another build of the same library (A/B measurements)
     if not os.path.exists(p):
         raise ImportError(f"{p} not found: build it with `python __graft_entry__.py build` "
                           "(mjpdes_b200 has no CPU fallback)")

@@ -54,7 +54,7 @@ struct mjp_handle {
   bool uploaded = false, launched = false, sweep = false;
   mjp::KParams kp{};
   // device buffers
-  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage, d_dur, d_rot;
+  DevBuf d_const, d_planes, d_out, d_scratch, d_partials, d_agg, d_log, d_logcur, d_cold, d_park, d_tapes, d_stage, d_dur, d_rot, d_first;
   // out-plane offsets inside d_out (bytes)
   size_t o_njobs = 0, o_res = 0, o_blk = 0, o_stv = 0, o_occ = 0, o_clk = 0, o_cur = 0, o_nev = 0, o_hash = 0,
          o_status = 0, out_bytes = 0, zero_bytes = 0;
@@ -217,7 +217,7 @@ void mjp_destroy(mjp_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_const, &h->d_planes, &h->d_out, &h->d_scratch, &h->d_partials, &h->d_agg, &h->d_log,
-                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage, &h->d_dur, &h->d_rot})
+                    &h->d_logcur, &h->d_cold, &h->d_park, &h->d_tapes, &h->d_stage, &h->d_dur, &h->d_rot, &h->d_first})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -431,8 +431,8 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     h->block_threads = threads;
     if (cold) {
       // STARTED[M] (read by every job movement) stays in shared memory when that costs no CTA per SM: the kernels run
-      // at most 12 (32-bit masks) / 8 (64-bit masks) CTAs per SM for their registers
-      const size_t reg_limit = kp.M > 32 ? 8 : 12;
+      // at most 12 (32-bit masks, statistics only) / 8 (64-bit masks, or with capture) CTAs per SM for their registers
+      const size_t reg_limit = (kp.M > 32 || h->want_log) ? 8 : 12;      // line_kernel_min_ctas
       const size_t without = std::min(reg_limit, h->smem_optin / (cta_bytes(true, threads) + 1024));
       mjp::KParams tmp = kp;
       tmp.started_hot = 1;
@@ -464,6 +464,11 @@ int mjp_launch_slice(mjp_handle *h, const mjp_rng_spec *rng, int want_log, doubl
     if (h->want_log) {                              // one tick of staged messages per instance; persists across slices
       CK(h->d_stage.reserve((size_t)kp.stage_cap * kp.n_inst * sizeof(unsigned long long)));
       kp.stage = h->d_stage.as<unsigned long long>();
+      // where the jobs were at each instance's first printed message (mjp_log_out.first_state); persists across slices
+      const size_t first_bytes = (size_t)2 * kp.M * kp.n_inst * sizeof(uint32_t);
+      CK(h->d_first.reserve(first_bytes));
+      kp.first_state = h->d_first.as<uint32_t>();
+      if (!resume) CK(cudaMemsetAsync(h->d_first.ptr, 0xFF, first_bytes, h->stream));
     }
     h->smem_bytes = (size_t)kp.const_bytes + per_thread * threads;
     int blocks = (int)((kp.n_inst + threads - 1) / threads);
@@ -610,6 +615,9 @@ static int download_impl(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log, uint
       log->count = take;
       log->dropped = dropped + (have - take);
       if (log->dropped) rc = MJP_LOG_TRUNCATED;
+      if (log->first_state)
+        CK(cudaMemcpyAsync(log->first_state + lo * 2 * (size_t)kp.M, h->d_first.ptr, (size_t)2 * kp.M * n * sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, h->stream));
     }
   }
   CK(cudaGetLastError());

@@ -86,6 +86,36 @@ __device__ __forceinline__ void nano_sleep(unsigned ns) {
 #endif
 }
 
+// hint: bring the line holding *p into the L1 (cold layouts: the flush issues these for every slot it is about to
+// read, so that its voted loops pay one L2 round trip together instead of one per trip)
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+#ifndef MJP_COLD32_LOG_MINBLOCKS
+#define MJP_COLD32_LOG_MINBLOCKS 8
+#endif
+#ifndef MJP_HOT32_MINBLOCKS
+#define MJP_HOT32_MINBLOCKS 6
+#endif
+// CTAs per SM each kernel family is compiled for, i.e. its register budget (65536 / (64 n), in steps of 8):
+//  * lines of up to 8 machines (MT > 0) and the 32-bit cold statistics kernel: 12 -> 80 registers.  The headline batch
+//    must be one wave, and the 10-machine sweep runs 12 CTAs per SM (measured: compiled for 8 it loses 23 %);
+//  * the 32-bit cold kernel WITH capture: 8 -> 128 registers.  Its shared memory holds 7-8 CTAs of the 20-machine
+//    line anyway, and at 80 registers the capture code spills (measured: C4 capture 275.6 -> 208.0 ms);
+//  * the 32-bit generic kernel with everything in shared memory (9..32 machines, one wave): shared memory holds at
+//    most 5-6 CTAs of it, so 6 -> 168 registers costs no residency;
+//  * 64-bit masks: 5 (all state in shared memory) / 7 (cold), as measured in round 1.
+__host__ __device__ constexpr int line_kernel_min_ctas(size_t mask_bytes, int mt, bool log, bool cold) {
+  return mask_bytes == 4 ? (mt > 0 ? 12 : (cold ? (log ? MJP_COLD32_LOG_MINBLOCKS : 12) : MJP_HOT32_MINBLOCKS)) : (cold ? 7 : 5);
+}
+#ifndef MJP_FLUSH_PREFETCH
+#define MJP_FLUSH_PREFETCH 0
+#endif
+
 // fire-and-forget add into an output plane
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 
@@ -101,17 +131,24 @@ struct LogTick {                       // what the records of one tick of one in
   uint32_t line_cnt, inst;
   int k;                               // records reserved for this tick
 };
-// record number q of the tick from staged word w (act | m << 8 | n << 16 | job << 32).
+// A staged message is laid out like the record's last two words so that emitting it is two register moves:
+// bits 0-31 the job number, bits 32-63 what follows `line` in the record: n | ord << 8 | act << 16 | m << 24
+// (ord = the message's index in :log-buf, i.e. its place in the tick's execution order).
+__device__ __forceinline__ unsigned long long stage_word(unsigned act, unsigned m, unsigned n, unsigned ord, uint32_t job) {
+  return (unsigned long long)job | ((unsigned long long)((n & 0xFFu) | ((ord & 0xFFu) << 8) | (act << 16) | (m << 24)) << 32);
+}
+__device__ __forceinline__ unsigned stage_act(unsigned long long w) { return ((unsigned)(w >> 32) >> 16) & 0xFFu; }
+__device__ __forceinline__ unsigned stage_m(unsigned long long w) { return (unsigned)(w >> 32) >> 24; }
+// record number q of the tick from staged word w.
 // Returns 0 = written, 1 = buffer full (dropped), 2 = more records than reserved.
 __device__ __forceinline__ int put_record(const LogTick &t, int q, unsigned long long w) {
   const unsigned long long at = t.base + (unsigned)q;
   if (q >= t.k) return 2;
   if (at >= t.capacity) return 1;
-  const unsigned act = (unsigned)w & 0xFFu;
+  const unsigned act = stage_act(w);
   const double aux = act == MJP_ACT_AJ ? t.aj_ends : (act == MJP_ACT_EJ ? t.ej_ent : __longlong_as_double(0x7FF8000000000000ll));
-  const unsigned long long w2 = (unsigned long long)(uint32_t)(w >> 32) | ((unsigned long long)t.inst << 32);
-  const unsigned long long w3 = (unsigned long long)(t.line_cnt + (uint32_t)q) | (((w >> 16) & 0x7FFFull) << 32) |
-                                ((w & 0xFFull) << 48) | (((w >> 8) & 0xFFull) << 56);
+  const unsigned long long w2 = (unsigned long long)(uint32_t)w | ((unsigned long long)t.inst << 32);
+  const unsigned long long w3 = (unsigned long long)(t.line_cnt + (uint32_t)q) | (w & 0xFFFFFFFF00000000ull);
   // two 16-byte streaming stores = one full 32-byte sector per record, not kept in L2
   double2 *dst = reinterpret_cast<double2 *>(t.out + at);
   __stcs(dst, make_double2(t.clk, aux));
@@ -134,9 +171,9 @@ __device__ __noinline__ unsigned emit_general(const LogTick t, const unsigned lo
     unsigned m;
     if (by_rank) {
       m = by_rank[a0];
-      for (a = 0; a < ns && ((unsigned)(stage[a] >> 8) & 0xFFu) != m; ++a) {}
+      for (a = 0; a < ns && stage_m(stage[a]) != m; ++a) {}
       if (a == ns) continue;                                 // this machine logged nothing in the tick
-    } else m = (unsigned)(stage[a] >> 8) & 0xFFu;
+    } else m = stage_m(stage[a]);
     const MaskT mbit = (MaskT)1 << m;
     if (done_m & mbit) continue;
     done_m |= mbit;
@@ -144,9 +181,9 @@ __device__ __noinline__ unsigned emit_general(const LogTick t, const unsigned lo
     int no = 0;
     unsigned have = 0;
     for (int b = a; b < ns; ++b) {
-      const unsigned wb = (unsigned)stage[b];
-      if (((wb >> 8) & 0xFFu) != m) continue;
-      const unsigned c = log_class(wb & 0xFFu);
+      const unsigned long long wb = stage[b];
+      if (stage_m(wb) != m) continue;
+      const unsigned c = log_class(stage_act(wb));
       if (!((have >> c) & 1u)) { have |= 1u << c; order |= c << (2 * no); ++no; }
     }
     for (int r = 0; r < no; ++r) {
@@ -154,7 +191,7 @@ __device__ __noinline__ unsigned emit_general(const LogTick t, const unsigned lo
       if ((c == 0u && (two_b & mbit)) || (c == 1u && (two_s & mbit))) continue;         // util/log.clj:51-53
       for (int b = a; b < ns; ++b) {
         const unsigned long long w = stage[b];
-        if (((unsigned)(w >> 8) & 0xFFu) != m || log_class((unsigned)w & 0xFFu) != c) continue;
+        if (stage_m(w) != m || log_class(stage_act(w)) != c) continue;
         const int rc = put_record(t, (int)q, w);
         dropped += rc == 1; bad |= rc == 2;
         ++q;
@@ -162,6 +199,16 @@ __device__ __noinline__ unsigned emit_general(const LogTick t, const unsigned lo
     }
   }
   return (q & 0xFFFFu) | ((dropped & 0x7FFFu) << 16) | (bad << 31);
+}
+
+// mjp_log_out.first_state: word i = number of the last job started on machine i, word M+i = bit 0 machine i holds a
+// job, bits 8-15 (count :holding) of buffer i.  Out of line: called once per instance.
+static __device__ __noinline__ void write_line_state(uint32_t *out, const uint32_t *started, uint32_t started_stride,
+                                                     const uint32_t *cnt, uint32_t cnt_stride, uint64_t occ, int M) {
+  for (int i = 0; i < M; ++i) {
+    out[i] = started[(size_t)i * started_stride];
+    out[M + i] = (uint32_t)((occ >> i) & 1u) | (i < M - 1 ? (cnt[(size_t)i * cnt_stride] & 0xFFu) << 8 : 0u);
+  }
 }
 
 // end-time (core.clj:138-151) split at the points where it needs an event that may not exist yet.
@@ -231,6 +278,9 @@ static __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid,
 }
 
 #define MJP_BIT(i) ((MaskT)1 << (i))
+#ifndef MJP_COLD_CONST_GLOBAL
+#define MJP_COLD_CONST_GLOBAL 1   /* 0: cold layouts copy lam / mu / w/W into shared memory too (A/B builds) */
+#endif
 #ifndef MJP_FIXED_NT
 #define MJP_FIXED_NT 64      /* CTA size of the MT > 0 variants (compile-time [slot][thread] strides) */
 #endif
@@ -242,20 +292,28 @@ static __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid,
 // SLICE: the launch may stop at a slice boundary and/or resume parked instances (mjp_launch_slice); kept out
 // of the plain variants because the park/unpark code keeps every state variable alive (4 % on the headline).
 template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SLICE, bool LOG, bool COLD = false>
-__global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) mjp_line_kernel(const KParams p) {
+__global__ void __launch_bounds__(64, line_kernel_min_ctas(sizeof(MaskT), MT, LOG, COLD)) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = (MT > 0) ? MJP_FIXED_NT : (int)blockDim.x, M = (MT > 0) ? MT : p.M, K = p.K;
 
   // ---- CTA constant table --------------------------------------------------
-  double *c_lam = reinterpret_cast<double *>(smem_raw);
-  double *c_mu = c_lam + M;
-  double *c_dur = c_mu + M;          // [K*M]  w/W  (job-requires, utils.clj:95-101)
-  double *c_thr = c_dur + K * M;     // [K]    new-job thresholds (core.clj:332-339)
+  // COLD lines of more than 32 machines: lam / mu / w/W are read where they lie in global memory, through the
+  // read-only path, by the few lanes that start a job or draw a sojourn -- for 50 machines x 16 job types the table
+  // is 7.2 KB of a 35 KB CTA, the difference between 6 and 8 CTAs per SM (mjp_plan.h: plan_const_bytes; measured:
+  // C5 quantum 57.2 -> 37.5 ms.  The 32-bit cold kernels gain no CTA from it and lose 1-4 %, so they keep the table)
+  constexpr bool CONST_GLOBAL = COLD && sizeof(MaskT) == 8 && MJP_COLD_CONST_GLOBAL;
+  double *s_lam = reinterpret_cast<double *>(smem_raw);
+  double *s_mu = s_lam + M;
+  double *s_dur = s_mu + M;          // [K*M]  w/W  (job-requires, utils.clj:95-101)
+  double *c_thr = CONST_GLOBAL ? s_lam : s_dur + K * M;     // [K]    new-job thresholds (core.clj:332-339)
+  const double *c_lam = CONST_GLOBAL ? p.lam : s_lam, *c_mu = CONST_GLOBAL ? p.mu : s_mu, *c_dur = CONST_GLOBAL ? p.dur : s_dur;
   int *c_N = reinterpret_cast<int *>(c_thr + K);
   int *c_lvl = c_N + M;
-  for (int q = tid; q < M; q += nt) { c_lam[q] = p.lam[q]; c_mu[q] = p.mu[q]; }
-  for (int q = tid; q < K * M; q += nt) c_dur[q] = p.dur[q];
+  if (!CONST_GLOBAL) {
+    for (int q = tid; q < M; q += nt) { s_lam[q] = p.lam[q]; s_mu[q] = p.mu[q]; }
+    for (int q = tid; q < K * M; q += nt) s_dur[q] = p.dur[q];
+  }
   for (int q = tid; q < K; q += nt) c_thr[q] = p.thr[q];
   for (int q = tid; q < M - 1; q += nt) { c_N[q] = p.N[q]; c_lvl[q] = p.lvl[q]; }
   __syncthreads();
@@ -348,8 +406,9 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
   enum { F_EJ = 1, F_TICK = 2, F_OVF = 4, F_PAUSE = 8, F_TAPE = 16, F_DURPL = 32, F_CAPPL = 64 };
   uint32_t flags = ((p.W_i || p.w_i) ? F_DURPL : 0u) | (p.N_i ? F_CAPPL : 0u);
   // line parameters, with the optional per-instance planes
-  auto lam_of = [&](int i) -> double { return (p.lam_i != nullptr) ? p.lam_i[(size_t)i * n_inst + g] : c_lam[i]; };
-  auto mu_of = [&](int i) -> double { return (p.mu_i != nullptr) ? p.mu_i[(size_t)i * n_inst + g] : c_mu[i]; };
+  auto cst = [&](const double *q) -> double { return CONST_GLOBAL ? __ldg(q) : *q; };
+  auto lam_of = [&](int i) -> double { return (p.lam_i != nullptr) ? p.lam_i[(size_t)i * n_inst + g] : cst(c_lam + i); };
+  auto mu_of = [&](int i) -> double { return (p.mu_i != nullptr) ? p.mu_i[(size_t)i * n_inst + g] : cst(c_mu + i); };
   auto cap_of = [&](int b) -> int { return (flags & F_CAPPL) ? p.N_i[(size_t)b * n_inst + g] : c_N[b]; };
   auto dur_of = [&](int k, int i) -> double {
     if (flags & F_DURPL) {
@@ -358,7 +417,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       const double Wv = p.W_i ? p.W_i[(size_t)i * n_inst + g] : p.W[i];
       return __ddiv_rn(wv, Wv);
     }
-    return c_dur[k * M + i];
+    return cst(c_dur + k * M + i);
   };
 
   double r_end[MT > 0 ? MT : 1] = {};
@@ -567,7 +626,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
   // [instance][slot]: the messages of an instance share cache lines with nobody else, so after the first
   // load of a tick the cleaning loops below run out of L1; rows beyond a tick's few messages are never
   // touched.  The capture costs no shared memory (same residency as a stats-only run).
-  // word: act | m << 8 | n << 16 | job << 32
+  // word: see stage_word
   unsigned long long *g_stage = LOG ? p.stage + (size_t)g * (size_t)p.stage_cap : nullptr;
   const int stage_cap = p.stage_cap;
   int n_staged = 0;
@@ -578,8 +637,7 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
     // :max-lines has been reached is never printed, so there is nothing to stage for it
     if (clock < p.warm_up || (uint64_t)line_cnt >= p.max_lines) return;
     if (n_staged < stage_cap)
-      g_stage[n_staged] = (unsigned long long)act | ((unsigned long long)m << 8) |
-                          ((unsigned long long)(n & 0x7FFF) << 16) | ((unsigned long long)job << 32);
+      g_stage[n_staged] = stage_word((unsigned)act, (unsigned)m, (unsigned)n, (unsigned)n_staged, job);
     else flags |= F_OVF;
     n_staged++;
   };
@@ -625,9 +683,10 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
     // (a tick in which more than 8 machines logged is regrouped in hash-map order: general routine)
     const bool wide = MT == 0 && MO::popc(seen) > 8;
     bool grouped = !wide;
-    for (int x = 0; __any_sync(fm, !wide && x < ns); ++x) if (!wide && x < ns) {
-      const unsigned long long w = g_stage[x];
-      const unsigned act = (unsigned)w & 0xFFu, m = (unsigned)(w >> 8) & 0xFFu, c = log_class(act);
+    const unsigned long long *sp = g_stage;                  // (a running pointer: the row address is not recomputed per trip)
+    for (int x = 0; __any_sync(fm, !wide && x < ns); ++x, ++sp) if (!wide && x < ns) {
+      const unsigned long long w = *sp;
+      const unsigned act = stage_act(w), m = stage_m(w), c = log_class(act);
       const MaskT mbit = MJP_BIT(m);
       if (m != pm) { if (gdone & mbit) grouped = false; gdone |= mbit; cdone = 0u; pm = m; pc = 3u; }
       if (c != pc) { if ((cdone >> c) & 1u) grouped = false; cdone |= 1u << c; pc = c; }
@@ -644,6 +703,11 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
     if (ns) {
       if (q != k) flags |= F_OVF;
       if (dropped) atomicAdd(p.log_cursor + 1, (unsigned long long)dropped);
+      // (log/detail model) util/log.clj:11-28: nothing before the warm-up reaches the record stream, so the host is
+      // told where the jobs were at the END of the tick that produced the instance's first records (the state has not
+      // moved since: this is the first logging micro-step after it, before its batch).  Once per instance, out of line.
+      if (line_cnt == 0u && k > 0 && p.first_state != nullptr)
+        write_line_state(p.first_state + (size_t)g * (size_t)(2 * M), st_base, st_stride, &CNT(0), (uint32_t)nt, (uint64_t)occ, M);
       line_cnt += (uint32_t)k;                               // util/log.clj:137
     }
     if (on) n_staged = 0;
@@ -666,6 +730,12 @@ __global__ void __launch_bounds__(64, sizeof(MaskT) == 4 ? 12 : (COLD ? 7 : 5)) 
       if (open0 && t0 == t0) red_add((is_s ? p.starved : p.blocked) + (size_t)i * n_inst + g, tick_clk - t0);
       *slot = open1 ? tick_clk : QNAN;
     };
+    if (COLD && MJP_FLUSH_PREFETCH) {
+      // cold layouts: :bs / :ss / :lastclk are read from the L2-resident scratch, one slot per trip of the loops below
+      for (MaskT q = warm ? pB : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; prefetch_l1(&BS(i)); }
+      for (MaskT q = warm ? pS : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; prefetch_l1(&SS(i)); }
+      for (MaskT q = warm ? touched : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int b = MO::ffs(q); q &= q - 1; prefetch_l1(&LASTCLK(b)); }
+    }
     if (MT > 0) {                                             // M <= 8: both masks fit one 32-bit word
       uint32_t q = warm ? ((uint32_t)pB | ((uint32_t)pS << 16)) : 0u;
       while (__any_sync(fm, q != 0)) if (q) {

@@ -53,6 +53,7 @@ struct KParams {
   void *log_records;      // mjp_log_record[log_capacity]
   uint64_t log_capacity;
   unsigned long long *log_cursor;   // [0] next free record, [1] records dropped
+  uint32_t *first_state;            // LOG mode, optional: [n_inst][2M] see mjp_log_out.first_state (nullptr: not wanted)
   unsigned long long *stage;        // LOG mode: [n_inst][stage_cap] messages of the current tick (global scratch)
   // shared-memory layout
   int32_t started_hot;    // cold layouts: STARTED[M] lives in shared memory after CNT (1) or in the cold scratch (0)

@@ -80,9 +80,19 @@ inline int cold_ends_slots(const KParams &kp) { return kp.M; }      // (allocate
 inline int cold_u32_slots(const KParams &kp, bool replay) {
   return 2 * kp.M + (kp.K > 1 ? (kp.R >> 2) : 0) + (replay ? kp.M : 0);      // no job-type ring for a single type
 }
+#ifndef MJP_COLD_CONST_GLOBAL
+#define MJP_COLD_CONST_GLOBAL 1
+#endif
+// CTA constant table: lam[M] mu[M] dur[K M] thr[K] N[M-1] lvl[M-1]; cold layouts of more than 32 machines keep only
+// thr / N / lvl on chip and read the rest from global memory (mjp_line_kernel.cuh)
+inline int plan_const_bytes(int M, int K, bool cold) {
+  const size_t f64 = (cold && M > 32 && MJP_COLD_CONST_GLOBAL) ? (size_t)K : (size_t)(2 * M + K * M + K);
+  return (int)plan_align_up(f64 * 8 + (size_t)2 * M * 4, 16);
+}
 inline size_t plan_layout(KParams &kp, bool ends_in_regs, bool replay, bool log, bool cold = false) {
   const int M = kp.M;
   (void)log;
+  kp.const_bytes = plan_const_bytes(M, kp.K, cold);
   const int groups = (M + 3) / 4;                                  // GS = 4
   const int ends_hot = (cold && kp.ends_cold) ? 0 : M;
   kp.nf64 = (cold ? 0 : cold_f64_slots(kp)) + 3 + (ends_in_regs ? 0 : ends_hot + 2 * groups);
@@ -124,7 +134,7 @@ inline LinePlan build_plan(const mjp_line_desc *L, uint64_t n_inst) {
     double accum = L->portion[0];
     for (int k = 0; k < K; ++k) { pl.cd.push_back(accum); accum = accum + L->portion[k]; }
   }
-  kp.const_bytes = (int)plan_align_up((size_t)(2 * M + K * M + K) * 8 + (size_t)2 * M * 4, 16);
+  kp.const_bytes = plan_const_bytes(M, K, false);
   // SCADA capture stages one tick of messages per instance.  A machine logs at most nine messages in a tick
   // (complete, start, :bl, :ub, :st, :us, :up, :down and a re-fired :up/:down); beyond the cap the instance ends
   // with MJP_INST_TICK_OVERFLOW.  The stage is a global scratch whose unused rows are never touched.

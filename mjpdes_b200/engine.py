@@ -17,8 +17,9 @@ class RunResult:
     """Per-instance ``*log-steady*`` content plus loop status, as numpy arrays."""
 
     def __init__(self, line: abi.HostLine, stats: abi.HostStats, log: np.ndarray | None, rc: int,
-                 kernel_ms: float, launches: int):
+                 kernel_ms: float, launches: int, first_state: np.ndarray | None = None):
         self.line, self.stats, self.log, self.rc = line, stats, log, rc
+        self.first_state = first_state          # [n_inst][2M], see mjp_log_out.first_state (SCADA capture only)
         self.kernel_ms, self.launches = kernel_ms, launches
 
     @property
@@ -79,12 +80,13 @@ class Handle:
         stats = abi.HostStats(line, n, want_hash=True, want_aggregate=want_aggregate)
         rng = abi.RngSpec(mode, 0, seed, first_instance_id)
         desc, st = line.desc(), stats.struct()
-        hlog = abi.HostLog(log_capacity) if log_capacity else None
+        hlog = abi.HostLog(log_capacity, n, line.M) if log_capacity else None
         rc = self._check(self._lib.mjp_run(self._h, C.byref(desc), n, C.byref(rng), C.byref(st),
                                            C.byref(hlog.struct()) if hlog else None),
                          allow=(abi.OK, abi.LOG_TRUNCATED))
         self._line, self._n = line, n
-        return RunResult(line, stats, hlog.view().copy() if hlog else None, rc, self.kernel_ms(), self.launch_count())
+        return RunResult(line, stats, hlog.view().copy() if hlog else None, rc, self.kernel_ms(), self.launch_count(),
+                         hlog.first_state if hlog else None)
 
     # -- device-resident variant (measurement) --------------------------------------
     def upload(self, line: abi.HostLine, n_inst: int):
@@ -128,15 +130,15 @@ class Handle:
     def download(self, stats: abi.HostStats | None = None, log_capacity: int = 0) -> RunResult:
         stats = stats or abi.HostStats(self._line, self._n)
         st = stats.struct()
-        hlog = abi.HostLog(log_capacity) if log_capacity else None
+        hlog = abi.HostLog(log_capacity, self._n, self._line.M) if log_capacity else None
         rc = self._check(self._lib.mjp_download(self._h, C.byref(st), C.byref(hlog.struct()) if hlog else None),
                          allow=(abi.OK, abi.LOG_TRUNCATED))
         return RunResult(self._line, stats, hlog.view().copy() if hlog else None, rc, self.kernel_ms(),
-                         self.launch_count())
+                         self.launch_count(), hlog.first_state if hlog else None)
 
     def log_count(self) -> tuple[int, int]:
         """(records captured, records dropped) by the last launch, without copying the records to the host."""
-        lo = abi.LogOut(None, (1 << 62), 0, 0)
+        lo = abi.LogOut(None, (1 << 62), 0, 0, None)
         self._check(self._lib.mjp_download(self._h, None, C.byref(lo)), allow=(abi.OK, abi.LOG_TRUNCATED))
         return int(lo.count), int(lo.dropped)
 

@@ -364,14 +364,14 @@ def analyze_results(cl: CompiledLine, stats: abi.HostStats, inst: int) -> dict:
 
 
 def postprocess_model(cl: CompiledLine, stats: abi.HostStats, inst: int, process_id: int, wall_seconds: float,
-                      log: np.ndarray | None = None) -> dict:
+                      log: np.ndarray | None = None, first_state=None) -> dict:
     """core.clj:708-718, plus the README's key aliases.  With ``:report {:diag-log-buf? true}`` the
     result carries ``:diag-log-buf``: every message print-lines saw, without ``:line`` (util/log.clj:134-135)."""
     r = analyze_results(cl, stats, inst)
     r[":process-id"] = process_id
     if (cl.model.get(":report") or {}).get(":diag-log-buf?"):
         from . import scada
-        msgs = scada.pull_data(cl, log, None, instance=inst) if log is not None else []
+        msgs = scada.pull_data(cl, log, None, instance=inst, first_state=first_state) if log is not None else []
         r[":diag-log-buf"] = [{k: v for k, v in m.items() if k != ":line"} for m in msgs]
     r[":jobmix"] = {jt: dict(cl.model[":jobmix"][jt]) for jt in cl.jobtypes}
     r[":status"] = abi.INST_STATUS_KEYWORD.get(int(stats.status[inst]), ":unknown")
@@ -418,11 +418,12 @@ def main_loop(model: dict, handle=None, out_stream=None, seed: int = DEFAULT_SEE
         if own:
             h.close()
     wall = time.time() - start
-    results = [postprocess_model(cl, res.stats, g, g if n > 1 else 1, wall, log=res.log) for g in range(n)]
+    results = [postprocess_model(cl, res.stats, g, g if n > 1 else 1, wall, log=res.log, first_state=res.first_state)
+               for g in range(n)]
     if out_stream is not None:
         out_stream.write("#_" + scada.pprint_edn(scada.pretty_model(model), print_length=10) + "\n")   # core.clj:750-752,773-775
         if res.log is not None:
-            for text in scada.render_lines(cl, res.log):
+            for text in scada.render_lines(cl, res.log, first_state=res.first_state):
                 out_stream.write(text + "\n")
         for r in results:                                                                 # util/log.clj:305-319
             out_stream.write(scada.result_block(r) + "\n")
@@ -456,6 +457,7 @@ class ContinuousModel:
         # a slice should yield a few hundred messages: ~1.4 events per machine per time unit
         self.dt = float(slice_time) if slice_time else max(1.0, 400.0 / (1.4 * self.cl.host.M))
         self.until, self.started, self.queue = 0.0, False, []
+        self._trackers = {}                                  # :job-detail?: the :dets state carried from slice to slice
         self.h.upload(self.cl.host, 1)
         self.h.reserve_log(self.capacity)
 
@@ -472,7 +474,7 @@ class ContinuousModel:
         if st != abi.INST_PAUSED:
             raise abi.MjpError(abi.ERR_INVALID, f"continuous run stopped with status {abi.INST_STATUS_KEYWORD.get(st, st)}")
         recs = np.sort(res.log, order="line")
-        self.queue.extend(scada.message_map(self.cl, r) for r in recs)
+        self.queue.extend(scada.message_maps(self.cl, recs, res.first_state, self._trackers))
 
     def pull_data(self, n: int) -> list:
         """core/pull-data! (core.clj:845-849): the next ``n`` messages."""

@@ -4,6 +4,7 @@
   shorten-msg-floats  util/log.clj:228-234   times re-read from their "~10,4f" rendering
   mjp2pretty-name     util/log.clj:248-261   :m1-start-job, :m2-complete-job, ...
   msg-key-order       util/log.clj:272-273   [:clk :act :m :mjpact :bf :jt :n :ent :ends :j :dets :line]
+  detail (:dets)      util/log.clj:11-28     job-per-machine / jobs-per-buffer snapshots, DetsTracker
   pretty-model        util/log.clj:293-303
 
 The device emits compact binary records (mjp_log_record); this module is the host-side
@@ -56,8 +57,101 @@ def shorten(x: float) -> float:
     return float(f"{x:.4f}")
 
 
-def message_map(cl, rec) -> dict:
-    """One record as the message map push-log hands to print-lines (keys in msg-key-order)."""
+_NO_DETS = object()
+
+
+def job_detail_mode(model: dict) -> str:
+    """How :dets shows in the printed messages.  log/detail reads [:report :job-detail?] (util/log.clj:14) while
+    push-log strips :dets unless the TOP-LEVEL :job-detail? is set (util/log.clj:101): "strip" (no :dets key),
+    "nil" (every message prints ``:dets nil``) or "full" (the snapshots)."""
+    if not model.get(":job-detail?"):
+        return "strip"
+    return "full" if (model.get(":report") or {}).get(":job-detail?") else "nil"
+
+
+class DetsTracker:
+    """(log/detail model), util/log.clj:11-28, for the messages of ONE instance: which job sits on which machine and
+    in which buffer just BEFORE each logged action.  Jobs pass through a serial line in order, so the state is the
+    number of the last job started per machine, which machines hold a job, and the buffer counts.  Nothing before the
+    warm-up is in the record stream, so the device reports that state once: ``mjp_log_out.first_state``, taken at the
+    END of the tick whose records are the instance's first; the moves of that tick are undone (in reverse execution
+    order) to get the state before it, and from there the state is advanced through the job movements in EXECUTION
+    order, which ``ord`` restores within a tick (clean-log-buf regroups a tick by machine; a cancelled :bl/:ub or
+    :st/:us pair moves no job)."""
+
+    def __init__(self, cl, first_state_row):
+        M = len(cl.machines)
+        row = [int(x) for x in first_state_row]
+        if len(row) != 2 * M or row[0] == 0xFFFFFFFF:
+            raise ValueError("first_state: nothing was printed for this instance")
+        self.cl, self.M = cl, M
+        self.started = row[:M]
+        self.occ = [bool(x & 1) for x in row[M:]]
+        self.cnt = [(x >> 8) & 0xFF for x in row[M:2 * M - 1]]
+        self._rewound = False                                     # first_state is the state AFTER the first tick
+
+    def snapshot(self) -> dict:
+        from . import cljhash
+        cl, M = self.cl, self.M
+        run = {cl.machines[i]: (self.started[i] if self.occ[i] else None) for i in range(M)}            # util/log.clj:18-22
+        bufs = {cl.buffers[b]: [self.started[b + 1] + 1 + q for q in range(self.cnt[b])] for b in range(M - 1)}   # :24-28
+        order = lambda d: {k: d[k] for k in cljhash.map_order(list(d.keys()))}                            # zipmap: a plain map
+        return {":run": order(run), ":bufs": order(bufs)}
+
+    def _apply(self, rec):
+        act, m = int(rec["act"]), int(rec["machine"])
+        if act in (abi.ACT_AJ, abi.ACT_SM):                       # add-job core.clj:240-254, advance2machine :263-277
+            self.started[m], self.occ[m] = int(rec["job"]), True
+            if act == abi.ACT_SM:
+                self.cnt[m - 1] -= 1
+        elif act == abi.ACT_BJ:                                   # advance2buffer core.clj:285-300
+            self.occ[m] = False
+            self.cnt[m] += 1
+        elif act == abi.ACT_EJ:
+            self.occ[m] = False
+
+    def _undo(self, rec):
+        act, m = int(rec["act"]), int(rec["machine"])
+        if act in (abi.ACT_AJ, abi.ACT_SM):                       # job j came after job j-1 on this machine
+            self.started[m], self.occ[m] = int(rec["job"]) - 1, False
+            if act == abi.ACT_SM:
+                self.cnt[m - 1] += 1
+        elif act == abi.ACT_BJ:
+            self.occ[m] = True
+            self.cnt[m] -= 1
+        elif act == abi.ACT_EJ:
+            self.occ[m] = True
+
+    def tick(self, recs) -> list:
+        """:dets of the records of one clock tick (given in cleaned order), in that order."""
+        ords = [int(r["ord"]) for r in recs]
+        if len(set(ords)) != len(ords):
+            raise ValueError("more than 256 messages in one clock tick: the 8-bit execution ordinal wrapped")
+        out = [None] * len(recs)
+        by_ord = sorted(range(len(recs)), key=lambda q: ords[q])
+        if not self._rewound:                                     # the instance's first tick: back to where it began
+            for q in reversed(by_ord):
+                self._undo(recs[q])
+            self._rewound = True
+        for q in by_ord:
+            out[q] = self.snapshot()
+            self._apply(recs[q])
+        return out
+
+    def run(self, recs) -> list:
+        """:dets for the records of this instance in :line order (any number of whole ticks)."""
+        out, a = [], 0
+        clk = recs["clk"].view(np.uint64) if len(recs) else []
+        for b in range(1, len(recs) + 1):
+            if b == len(recs) or clk[b] != clk[a]:
+                out.extend(self.tick(recs[a:b]))
+                a = b
+        return out
+
+
+def message_map(cl, rec, dets=_NO_DETS) -> dict:
+    """One record as the message map push-log hands to print-lines (keys in msg-key-order).  ``dets``: the value
+    of :dets when the model keeps it (None prints as nil)."""
     act, m = int(rec["act"]), int(rec["machine"])
     mname = cl.machines[m]
     out = {":clk": shorten(float(rec["clk"])), ":act": f"{mname}-{_PRETTY[act]}", ":m": mname,
@@ -76,6 +170,8 @@ def message_map(cl, rec) -> dict:
         out[":ends"] = shorten(float(rec["aux"]))
     if act in (abi.ACT_AJ, abi.ACT_BJ, abi.ACT_EJ, abi.ACT_SM):
         out[":j"] = int(rec["job"])
+    if dets is not _NO_DETS:
+        out[":dets"] = dets
     out[":line"] = int(rec["line"])
     return out
 
@@ -83,7 +179,35 @@ def message_map(cl, rec) -> dict:
 def _show(v) -> str:
     if isinstance(v, float):
         return java_double(v)
+    if v is None or isinstance(v, dict):
+        return _flat(v)                  # ~A of nil / of a map: print-str
     return str(v)
+
+
+def message_maps(cl, recs, first_state=None, trackers: dict | None = None) -> list:
+    """Message maps of records sorted by (instance, line), with :dets as the model's :job-detail? flags say
+    (job_detail_mode).  ``first_state``: RunResult.first_state; ``trackers``: {instance: DetsTracker} carried over
+    between successive parts of one stream (streaming)."""
+    mode = job_detail_mode(cl.model)
+    if mode == "strip":
+        return [message_map(cl, r) for r in recs]
+    if mode == "nil":
+        return [message_map(cl, r, None) for r in recs]
+    if first_state is None:
+        raise ValueError(":job-detail? needs RunResult.first_state")
+    trackers = {} if trackers is None else trackers
+    out = []
+    inst = recs["instance"] if len(recs) else []
+    a = 0
+    for b in range(1, len(recs) + 1):
+        if b == len(recs) or inst[b] != inst[a]:
+            g = int(inst[a])
+            if g not in trackers:
+                trackers[g] = DetsTracker(cl, first_state[g])
+            part = recs[a:b]
+            out.extend(message_map(cl, r, d) for r, d in zip(part, trackers[g].run(part)))
+            a = b
+    return out
 
 
 def format_line(msg: dict) -> str:
@@ -92,18 +216,18 @@ def format_line(msg: dict) -> str:
     return "{:clk%10.4f :act %-18s %s}" % (msg[":clk"], msg[":act"], rest)
 
 
-def render_lines(cl, records: np.ndarray, instance: int | None = None):
+def render_lines(cl, records: np.ndarray, instance: int | None = None, first_state=None):
     """Text lines of one instance (default: every instance, in instance order), in :line order."""
     recs = np.sort(records, order=["instance", "line"])
     if instance is not None:
         recs = recs[recs["instance"] == instance]
-    return [format_line(message_map(cl, r)) for r in recs]
+    return [format_line(m) for m in message_maps(cl, recs, first_state)]
 
 
-def pull_data(cl, records: np.ndarray, n: int | None, instance: int = 0):
+def pull_data(cl, records: np.ndarray, n: int | None, instance: int = 0, first_state=None):
     """core/pull-data! (core.clj:845-849) over a captured stream: the first n message maps (all if n is None)."""
-    recs = np.sort(records[records["instance"] == instance], order="line")[:n]
-    return [message_map(cl, r) for r in recs]
+    recs = np.sort(records[records["instance"] == instance], order="line")
+    return message_maps(cl, recs, first_state)[:n]
 
 
 # defrecord field lists (core.clj:38-66): a record prints its declared fields first, in this order and nil when unset,

@@ -34,7 +34,8 @@ class Extra(C.Structure):
     _fields_ = [("act_counts", C.POINTER(C.c_uint64)), ("iterations", C.POINTER(C.c_uint64)),
                 ("ticks", C.POINTER(C.c_uint64)), ("max_tick_msgs", C.POINTER(C.c_uint32)),
                 ("max_lookahead", C.POINTER(C.c_uint32)), ("wide_ticks", C.POINTER(C.c_uint64)),
-                ("wide_ticks_reordered", C.POINTER(C.c_uint64))]
+                ("wide_ticks_reordered", C.POINTER(C.c_uint64)), ("dets", C.POINTER(C.c_int64)),
+                ("dets_capacity", C.c_uint64), ("dets_len", C.POINTER(C.c_uint64))]
 
 
 class Basics(C.Structure):
@@ -81,19 +82,23 @@ def lib() -> C.CDLL:
 
 
 class OracleResult:
-    def __init__(self, stats: abi.HostStats, log: np.ndarray | None, extra: dict, rc: int):
+    def __init__(self, stats: abi.HostStats, log: np.ndarray | None, extra: dict, rc: int, first_state=None, dets=None):
         self.stats, self.log, self.extra, self.rc = stats, log, extra, rc
+        self.first_state = first_state      # [n][2M], mjp_log_out.first_state
+        self.dets = dets                    # job_detail: one (run, bufs) pair per record, the literal log/detail snapshots
 
 
 def run(line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int = 0, first_instance_id: int = 0,
-        log_capacity: int = 0, n_threads: int = 1, tapes: abi.DrawTapes | None = None) -> OracleResult:
-    """main-loop-loop (core.clj:729-744) for ``n_inst`` instances on the CPU."""
+        log_capacity: int = 0, n_threads: int = 1, tapes: abi.DrawTapes | None = None,
+        job_detail: bool = False) -> OracleResult:
+    """main-loop-loop (core.clj:729-744) for ``n_inst`` instances on the CPU.  ``job_detail``: [:report :job-detail?],
+    every printed message comes with its literal (log/detail model) snapshot (util/log.clj:11-28)."""
     l = lib()
     n = int(n_inst)
     stats = abi.HostStats(line, n)
     rng = abi.RngSpec(mode, 0, seed, first_instance_id)
     desc = line.desc()
-    hlog = abi.HostLog(log_capacity) if log_capacity else None
+    hlog = abi.HostLog(log_capacity, n, line.M) if log_capacity else None
     ex = dict(act_counts=np.zeros((10, n), np.uint64), iterations=np.zeros(n, np.uint64),
               ticks=np.zeros(n, np.uint64), max_tick_msgs=np.zeros(n, np.uint32),
               max_lookahead=np.zeros(n, np.uint32), wide_ticks=np.zeros(n, np.uint64),
@@ -102,6 +107,12 @@ def run(line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int 
               abi.ptr(ex["ticks"], C.c_uint64), abi.ptr(ex["max_tick_msgs"], C.c_uint32),
               abi.ptr(ex["max_lookahead"], C.c_uint32), abi.ptr(ex["wide_ticks"], C.c_uint64),
               abi.ptr(ex["wide_ticks_reordered"], C.c_uint64))
+    dets_buf, dets_len = None, C.c_uint64(0)
+    if job_detail and hlog:
+        M = line.M
+        per = 2 * M + int(np.sum(line.N)) + M                 # a snapshot never holds more ids than the line holds jobs
+        dets_buf = np.zeros(max(1, int(log_capacity) * per), np.int64)
+        e.dets, e.dets_capacity, e.dets_len = abi.ptr(dets_buf, C.c_int64), len(dets_buf), C.pointer(dets_len)
     s = stats.struct()
     ts = tapes.struct() if tapes is not None else None
     l.mjpo_set_tapes(C.byref(ts) if ts is not None else None)
@@ -110,7 +121,20 @@ def run(line: abi.HostLine, n_inst: int, mode: int = abi.RNG_COUNTER, seed: int 
     l.mjpo_set_tapes(None)
     if rc not in (abi.OK, abi.LOG_TRUNCATED):
         raise abi.MjpError(rc, "oracle rejected the descriptor")
-    return OracleResult(stats, hlog.view().copy() if hlog else None, ex, rc)
+    dets = None
+    if dets_buf is not None:
+        assert dets_len.value <= len(dets_buf)
+        dets, q, M = [], 0, line.M
+        while q < dets_len.value:
+            run_ = [int(x) if x >= 0 else None for x in dets_buf[q:q + M]]
+            q += M
+            bufs = []
+            for _ in range(M - 1):
+                c = int(dets_buf[q])
+                bufs.append([int(x) for x in dets_buf[q + 1:q + 1 + c]])
+                q += 1 + c
+            dets.append((run_, bufs))
+    return OracleResult(stats, hlog.view().copy() if hlog else None, ex, rc, hlog.first_state if hlog else None, dets)
 
 
 def record_tapes(line: abi.HostLine, n_inst: int, seed: int, len_jobtype: int, len_uniform: int, len_exp: int,

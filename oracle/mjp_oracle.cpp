@@ -30,6 +30,7 @@
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <memory>
 #include <string>
 #include <utility>
 #include <thread>
@@ -284,7 +285,12 @@ struct Machine {
 };
 
 struct Msg {             /* one log message map */
-  uint8_t act; int m; int64_t j; int n; double aux; double clk;
+  uint8_t act = 0; int m = 0; int64_t j = 0; int n = 0; double aux = 0.0; double clk = 0.0;
+  Msg() = default;
+  Msg(uint8_t act_, int m_, int64_t j_, int n_, double aux_, double clk_) : act(act_), m(m_), j(j_), n(n_), aux(aux_), clk(clk_) {}
+  int ord = 0;           /* its index in :log-buf among the messages of its tick (execution order) */
+  /* :dets (log/detail, log:11-28), flattened: the M values of :run (-1 = nil), then per buffer (count, ids...) */
+  std::shared_ptr<std::vector<int64_t>> dets;
 };
 
 struct Steady {          /* log:144-152 */
@@ -325,6 +331,14 @@ struct Sim {
   /* SCADA sink */
   std::vector<mjp_log_record> *sink = nullptr;
   uint32_t inst_index = 0;
+  /* [:report :job-detail?] (log:14): messages carry :dets; the printed ones are appended to dets_sink */
+  bool job_detail = false;
+  std::vector<int64_t> *dets_sink = nullptr;
+  /* where the jobs were after the tick that is printed first (mjp_log_out.first_state) */
+  std::vector<int64_t> started;       /* number of the last job started on machine i */
+  uint32_t *first_state = nullptr;    /* ... = the state at the END of the tick whose records are printed first */
+  std::vector<uint32_t> tick_end_state;
+  bool have_first = false;
 
   /* ---- utils.clj ---- */
   bool up(int i) const { return mach[i].has_future && mach[i].future.kind == EV_DOWN; }   /* utils:60-62 */
@@ -351,10 +365,32 @@ struct Sim {
     if (act == MJP_ACT_EJ) hash = (hash ^ d2b(aux2)) * 0x100000001b3ull;
   }
 
+  /* ---- log/detail, log:11-28: which job is on which machine / in which buffer, BEFORE the action is applied ---- */
+  std::shared_ptr<std::vector<int64_t>> detail() const {
+    if (!job_detail) return nullptr;                          /* log:14 */
+    auto d = std::make_shared<std::vector<int64_t>>();
+    for (int i = 0; i < M; ++i) d->push_back(mach[i].occ ? mach[i].job.id : -1);   /* (-> ... :status :id), log:19-22 */
+    for (int b = 0; b < M - 1; ++b) {                                              /* (mapv :id :holding), log:25-28 */
+      d->push_back((int64_t)holding[b].size());
+      for (const Job &j : holding[b]) d->push_back(j.id);
+    }
+    return d;
+  }
   /* ---- log/log, log:30-36 ---- */
-  void log(const Msg &msg) {
+  void log(Msg msg) {
     bool keep = up_down || !(msg.act == MJP_ACT_UP || msg.act == MJP_ACT_DOWN);
-    if (keep) log_buf.push_back(msg);
+    if (!keep) return;
+    msg.dets = detail();
+    if (first_state && !have_first && (log_buf.empty() || msg.clk != log_buf.back().clk)) {
+      /* first message of a new tick, logged before its action is applied: the jobs are where the previous tick
+       * left them.  Kept until push-log prints that tick (below). */
+      tick_end_state.assign(2 * (size_t)M, 0u);
+      for (int i = 0; i < M; ++i) {
+        tick_end_state[i] = (uint32_t)started[i];
+        tick_end_state[M + i] = (mach[i].occ ? 1u : 0u) | (i < M - 1 ? (uint32_t)holding[i].size() << 8 : 0u);
+      }
+    }
+    log_buf.push_back(msg);
   }
 
   /* first event with etime >= clock: the drop-while of core:143 and core:198 */
@@ -402,7 +438,7 @@ struct Sim {
     count_event(MJP_ACT_AJ, i, j.id, j.type, clock, ends);
     log({MJP_ACT_AJ, i, j.id, j.type, ends, clock});
     current_job++;
-    mach[i].occ = true; mach[i].job = j;
+    mach[i].occ = true; mach[i].job = j; started[i] = j.id;
     set_machine_future(i);
   }
   void advance2machine(int i) {                          /* core:263-277 */
@@ -412,7 +448,7 @@ struct Sim {
     j.ends = end_time(job_requires(j, i), i);
     count_event(MJP_ACT_SM, i, j.id, (int)h.size(), clock, j.ends);
     log({MJP_ACT_SM, i, j.id, (int)h.size(), kNaN, clock});
-    mach[i].occ = true; mach[i].job = j;
+    mach[i].occ = true; mach[i].job = j; started[i] = j.id;
     set_machine_future(i);
     h.pop_front();
   }
@@ -591,8 +627,9 @@ struct Sim {
       for (const Msg &m : clean) {
         mjp_log_record r;
         r.clk = m.clk; r.aux = m.aux; r.job = (uint32_t)m.j; r.instance = inst_index;
-        r.line = (uint32_t)line++; r.n = (uint16_t)m.n; r.act = m.act; r.machine = (uint8_t)m.m;
+        r.line = (uint32_t)line++; r.n = (uint8_t)m.n; r.ord = (uint8_t)m.ord; r.act = m.act; r.machine = (uint8_t)m.m;
         sink->push_back(r);
+        if (dets_sink && m.dets) dets_sink->insert(dets_sink->end(), m.dets->begin(), m.dets->end());
       }
     }
     line_cnt += clean.size();                                   /* log:137 */
@@ -607,6 +644,7 @@ struct Sim {
     if (max_time > min_time) {                                  /* log:98 */
       std::vector<Msg> now, later, clean;
       for (const Msg &m : log_buf) (m.clk == min_time ? now : later).push_back(m);
+      for (size_t q = 0; q < now.size(); ++q) now[q].ord = (int)q;
       const bool by_hash = distinct_machines(now) > 8;          /* array-map -> hash-map promotion (D1) */
       clean_log_buf(now, clean, by_hash);                       /* log:100-102 */
       if (by_hash && min_time >= warm_up) {
@@ -620,6 +658,10 @@ struct Sim {
       }
       if (min_time >= warm_up) for (const Msg &m : clean) add_compute_log(m);   /* log:104-105 */
       bool print_now = log_on && !clean.empty() && max_lines > line_cnt && min_time >= warm_up; /* log:220-226 */
+      if (print_now && first_state && !have_first) {            /* mjp_log_out.first_state */
+        have_first = true;
+        for (size_t q = 0; q < tick_end_state.size(); ++q) first_state[q] = tick_end_state[q];
+      }
       if (print_now) print_lines(clean);
       log_buf.swap(later);                                      /* log:108 */
     }
@@ -692,7 +734,7 @@ void build_sim(Sim &s, const mjp_line_desc *L, uint64_t n_inst, uint64_t g, cons
   s.M = L->M; s.K = L->K;
   s.draws.seed = rng->seed; s.draws.inst = rng->first_instance_id + g;
   s.mach.resize(s.M); s.N.resize(s.M > 1 ? s.M - 1 : 0); s.holding.resize(s.N.size());
-  s.blocked.assign(s.M, 0); s.starved.assign(s.M, 0);
+  s.blocked.assign(s.M, 0); s.starved.assign(s.M, 0); s.started.assign(s.M, 0);
   s.portion.assign(L->portion, L->portion + s.K);
   s.w.resize((size_t)s.K * s.M);
   for (int q = 0; q < s.K * s.M; ++q) s.w[q] = L->w_inst ? L->w_inst[(size_t)q * n_inst + g] : L->w[q];
@@ -796,6 +838,8 @@ int mjpo_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng,
   if (n_threads < 1) n_threads = 1;
   if ((uint64_t)n_threads > n_inst) n_threads = (int)(n_inst ? n_inst : 1);
   std::vector<std::vector<mjp_log_record>> sinks(n_inst && log && log->records ? n_inst : 0);
+  const bool want_dets = extra && extra->dets && !sinks.empty();
+  std::vector<std::vector<int64_t>> dets_sinks(want_dets ? n_inst : 0);
   std::atomic<uint64_t> next(0);
   auto worker = [&]() {
     for (;;) {
@@ -805,6 +849,11 @@ int mjpo_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng,
       build_sim(s, L, n_inst, g, rng);
       s.inst_index = (uint32_t)g;
       if (!sinks.empty()) s.sink = &sinks[g];
+      if (want_dets) { s.job_detail = true; s.dets_sink = &dets_sinks[g]; }
+      if (log && log->first_state) {
+        s.first_state = log->first_state + (size_t)g * 2 * (size_t)L->M;
+        for (int q = 0; q < 2 * L->M; ++q) s.first_state[q] = 0xFFFFFFFFu;
+      }
       s.main_loop_loop();
       store_stats(s, L, n_inst, g, stats);
       if (extra) {
@@ -831,6 +880,11 @@ int mjpo_run(const mjp_line_desc *L, uint64_t n_inst, const mjp_rng_spec *rng,
       if (log->count < log->capacity) log->records[log->count++] = r; else log->dropped++;
     }
     if (log->dropped) rc = MJP_LOG_TRUNCATED;
+  }
+  if (want_dets) {                                              /* same order as the records; truncated like them */
+    uint64_t len = 0;
+    for (auto &v : dets_sinks) for (int64_t x : v) { if (len < extra->dets_capacity) extra->dets[len] = x; ++len; }
+    if (extra->dets_len) *extra->dets_len = len;
   }
   if (stats && stats->aggregate && stats->njobs && stats->residence_sum && stats->blocked_time &&
       stats->starved_time && stats->occ_time && stats->status) {

@@ -35,6 +35,12 @@ typedef struct mjpo_extra {
   uint32_t *max_lookahead;  /* [n] deepest end-time look-ahead (events past :future) */
   uint64_t *wide_ticks;     /* [n] post-warm-up ticks in which more than 8 machines logged (hash-map regrouping) */
   uint64_t *wide_ticks_reordered; /* [n] ... of which the cleaned batch differs from first-appearance grouping */
+  /* [:report :job-detail?] (util/log.clj:11-28): non-NULL turns the :dets snapshots on; those of the PRINTED messages
+   * are written here in record order, each flattened as the M values of :run (-1 = nil) followed, per buffer, by
+   * (count :holding) and the job ids.  dets_len receives the words produced (may exceed dets_capacity).  */
+  int64_t  *dets;
+  uint64_t  dets_capacity;
+  uint64_t *dets_len;
 } mjpo_extra;
 
 /* Position of `name` (a keyword without colon or namespace, e.g. "m7") in Clojure hash-map iteration order is

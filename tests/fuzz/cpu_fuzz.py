@@ -92,8 +92,9 @@ def one(trial: int):
     if log:
         a, b = np.sort(got.log, order=["instance", "line"]), np.sort(want.log, order=["instance", "line"])
         assert len(a) == len(b)
-        assert all(np.array_equal(a[f], b[f]) for f in ("clk", "job", "line", "n", "act", "machine"))
+        assert all(np.array_equal(a[f], b[f]) for f in ("clk", "job", "line", "n", "ord", "act", "machine"))
         assert np.array_equal(a["aux"].view(np.uint64), b["aux"].view(np.uint64))
+        assert np.array_equal(got.first_state, want.first_state), "first_state"
     return M, K, mode, cold, slices, log
 
 

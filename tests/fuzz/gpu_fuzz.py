@@ -60,9 +60,10 @@ with engine.Handle(device=0, event_hash=True) as h:
                 if got.rc == abi.OK:
                     a = np.sort(got.log, order=["instance", "line"]); b = np.sort(want.log, order=["instance", "line"])
                     assert len(a) == len(b)
-                    for f in ("clk", "job", "line", "n", "act", "machine"):
+                    for f in ("clk", "job", "line", "n", "ord", "act", "machine"):
                         assert np.array_equal(a[f], b[f]), f
                     assert np.array_equal(a["aux"].view(np.uint64), b["aux"].view(np.uint64))
+                    assert np.array_equal(got.first_state, want.first_state), "first_state"
             ok += 1
         except Exception as e:
             fails.append((trial, M, K, mode, n, log, slices, str(e)[:160]))

@@ -34,14 +34,15 @@ static int run_case(int M, int K, int n, double run_to, int mode, bool log, bool
   mjp_stats_out s{njobs.data(), res.data(), blk.data(), stv.data(), occ.data(), clk.data(), cur.data(), nev.data(),
                   hash.data(), status.data(), agg.data()};
   std::vector<mjp_log_record> recs(log ? 400000 : 1);
-  mjp_log_out lo{recs.data(), recs.size(), 0, 0};
+  mjp_log_out lo{recs.data(), recs.size(), 0, 0, nullptr};
   mjp_rng_spec rng{mode, 0, 0x4D4A50646573ull, 0};
   // poison what the chosen layout does not use of the shared-memory arena
   {
     mjp::LinePlan pl = mjp::build_plan(&L, n);
     mjp::KParams kp = pl.kp;
     const bool mt = !cold && !log && M <= 8;
-    const size_t used = kp.const_bytes + mjp::plan_layout(kp, mt, mode != MJP_RNG_COUNTER, log, cold);
+    const size_t per_thread = mjp::plan_layout(kp, mt, mode != MJP_RNG_COUNTER, log, cold);   // (sets kp.const_bytes)
+    const size_t used = kp.const_bytes + per_thread;
     ASAN_UNPOISON_MEMORY_REGION(mjp::smem_raw, sizeof(mjp::smem_raw));
     ASAN_POISON_MEMORY_REGION(mjp::smem_raw + used, sizeof(mjp::smem_raw) - used);
   }

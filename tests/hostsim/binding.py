@@ -45,7 +45,7 @@ def run(line, n_inst, mode=abi.RNG_COUNTER, seed=0, first_instance_id=0, want_ha
         slices=(), tapes=None, rotation=0, started_hot=None):
     stats = abi.HostStats(line, n_inst)
     d, r, s = line.desc(), abi.RngSpec(mode, 0, seed, first_instance_id), stats.struct()
-    hlog = abi.HostLog(log_capacity) if log_capacity else None
+    hlog = abi.HostLog(log_capacity, n_inst, line.M) if log_capacity else None
     sl = np.ascontiguousarray(slices, np.float64)
     lib().hostsim_set_rotation(int(rotation))
     # cold layouts: STARTED[M] in shared memory or in the scratch; by default alternate with the batch size so that
@@ -60,6 +60,7 @@ def run(line, n_inst, mode=abi.RNG_COUNTER, seed=0, first_instance_id=0, want_ha
     if hlog:
         stats.log = hlog.view().copy()
         stats.log_dropped = hlog.dropped
+        stats.first_state = hlog.first_state
     return stats
 
 

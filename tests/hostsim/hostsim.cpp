@@ -65,6 +65,10 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   const bool want_log = log && L->log;
   std::vector<unsigned long long> stage(want_log ? (size_t)kp.stage_cap * n_inst : 0);
   if (want_log) { kp.log_records = log->records; kp.log_capacity = log->capacity; kp.log_cursor = cursor; kp.stage = stage.data(); }
+  if (want_log && log->first_state) {
+    kp.first_state = log->first_state;
+    for (size_t q = 0; q < (size_t)2 * M * n_inst; ++q) kp.first_state[q] = 0xFFFFFFFFu;
+  }
   kp.park_words = 72 + 2 * kp.nf64 + kp.nu32;
   std::vector<uint32_t> park((size_t)kp.park_words * n_inst);
   kp.park = park.data();

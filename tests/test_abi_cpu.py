@@ -54,8 +54,9 @@ def test_struct_layout_matches_header(tmp_path):
         "mjp_stats_out": (abi.StatsOut, {"njobs": "njobs", "occ_time": "occ_time", "event_hash": "event_hash",
                                          "status": "status", "aggregate": "aggregate"}),
         "mjp_log_record": (abi.LogRecord, {"clk": "clk", "aux": "aux", "job": "job", "instance": "instance",
-                                           "line": "line", "n": "n", "act": "act", "machine": "machine"}),
-        "mjp_log_out": (abi.LogOut, {"records": "records", "capacity": "capacity", "count": "count", "dropped": "dropped"}),
+                                           "line": "line", "n": "n", "ord": "ord", "act": "act", "machine": "machine"}),
+        "mjp_log_out": (abi.LogOut, {"records": "records", "capacity": "capacity", "count": "count", "dropped": "dropped",
+                                     "first_state": "first_state"}),
         "mjp_config": (abi.Config, {"device": "device", "flags": "flags", "max_instances": "max_instances"}),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]

@@ -12,6 +12,10 @@ if has tests; then
   timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_tests.log 2>&1; echo "tests exit $?" >> $O/${TAG}_tests.log
   tail -5 $O/${TAG}_tests.log
 fi
+if has tests_sel; then   # a subset: TESTS="tests/test_x.py -k expr"
+  timeout 1200 python -m pytest $TESTS -m gpu -x -q > $O/${TAG}_tests_sel.log 2>&1; echo "tests_sel exit $?" >> $O/${TAG}_tests_sel.log
+  tail -5 $O/${TAG}_tests_sel.log
+fi
 if has bench; then
   timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench exit $?"
   tail -c 600 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err
@@ -32,6 +36,14 @@ if has ab_persist; then
     done
   done > $O/${TAG}_ab_persist.log 2>&1
   cat $O/${TAG}_ab_persist.log
+fi
+if has ab_lib; then     # the shipped library against a second build of it (mjpdes_b200/csrc/ab/, see the Makefile)
+  for c in ${AB_CONFIGS:-C5_long50_slice C5_long50 C4_mixed20_stats_many C3_sweep10 C4_mixed20_scada_many example_scada C2_example}; do
+    for lib in "" mjpdes_b200/csrc/ab*/libmjpdes_b200.so; do
+      echo -n "lib=${lib:-shipped} $c: "; MJP_LIB=$lib timeout 600 python tools/profile_config.py $c 2>&1 | tail -1
+    done
+  done > $O/${TAG}_ab_lib.log 2>&1
+  cat $O/${TAG}_ab_lib.log
 fi
 if has cliff; then
   MJP_ROTATE=0 timeout 600 python tools/cliff_probe.py > $O/${TAG}_cliff_norotate.json 2> $O/${TAG}_cliff_norotate.err; echo "cliff0 exit $?"
