@@ -86,35 +86,32 @@ __device__ __forceinline__ void nano_sleep(unsigned ns) {
 #endif
 }
 
-// hint: bring the line holding *p into the L1 (cold layouts: the flush issues these for every slot it is about to
-// read, so that its voted loops pay one L2 round trip together instead of one per trip)
-__device__ __forceinline__ void prefetch_l1(const void *p) {
-#ifdef __CUDA_ARCH__
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
 #ifndef MJP_COLD32_LOG_MINBLOCKS
 #define MJP_COLD32_LOG_MINBLOCKS 8
+#endif
+#ifndef MJP_MT_LOG_MINBLOCKS
+#define MJP_MT_LOG_MINBLOCKS 10
+#endif
+#ifndef MJP_EMIT_RUNNING_POINTER
+#define MJP_EMIT_RUNNING_POINTER 1
 #endif
 #ifndef MJP_HOT32_MINBLOCKS
 #define MJP_HOT32_MINBLOCKS 6
 #endif
 // CTAs per SM each kernel family is compiled for, i.e. its register budget (65536 / (64 n), in steps of 8):
 //  * lines of up to 8 machines (MT > 0) and the 32-bit cold statistics kernel: 12 -> 80 registers.  The headline batch
-//    must be one wave, and the 10-machine sweep runs 12 CTAs per SM (measured: compiled for 8 it loses 23 %);
+//    fits one wave that way, and the 10-machine sweep runs 12 CTAs per SM (measured: compiled for 8 it loses 23 %);
+//  * lines of up to 8 machines WITH capture, or replaying the reference's draw loop (REPLAY / TAPE): 10 -> 96
+//    registers.  At 80 that code spills; a batch that no longer fits one wave is rotated (measured on example.clj
+//    with capture, 104 192 instances: 41.2 -> 38.4 ms);
 //  * the 32-bit cold kernel WITH capture: 8 -> 128 registers.  Its shared memory holds 7-8 CTAs of the 20-machine
 //    line anyway, and at 80 registers the capture code spills (measured: C4 capture 275.6 -> 208.0 ms);
 //  * the 32-bit generic kernel with everything in shared memory (9..32 machines, one wave): shared memory holds at
 //    most 5-6 CTAs of it, so 6 -> 168 registers costs no residency;
 //  * 64-bit masks: 5 (all state in shared memory) / 7 (cold), as measured in round 1.
-__host__ __device__ constexpr int line_kernel_min_ctas(size_t mask_bytes, int mt, bool log, bool cold) {
-  return mask_bytes == 4 ? (mt > 0 ? 12 : (cold ? (log ? MJP_COLD32_LOG_MINBLOCKS : 12) : MJP_HOT32_MINBLOCKS)) : (cold ? 7 : 5);
+__host__ __device__ constexpr int line_kernel_min_ctas(size_t mask_bytes, int mt, bool log, bool cold, bool replay) {
+  return mask_bytes == 4 ? (mt > 0 ? ((log || replay) ? MJP_MT_LOG_MINBLOCKS : 12) : (cold ? (log ? MJP_COLD32_LOG_MINBLOCKS : 12) : MJP_HOT32_MINBLOCKS)) : (cold ? 7 : 5);
 }
-#ifndef MJP_FLUSH_PREFETCH
-#define MJP_FLUSH_PREFETCH 0
-#endif
 
 // fire-and-forget add into an output plane
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
@@ -292,7 +289,7 @@ static __device__ MJP_NOINLINE void jobtype_uniforms(uint32_t blk, uint64_t gid,
 // SLICE: the launch may stop at a slice boundary and/or resume parked instances (mjp_launch_slice); kept out
 // of the plain variants because the park/unpark code keeps every state variable alive (4 % on the headline).
 template <typename MaskT, int MT, bool REPLAY, bool HASH, bool SLICE, bool LOG, bool COLD = false>
-__global__ void __launch_bounds__(64, line_kernel_min_ctas(sizeof(MaskT), MT, LOG, COLD)) mjp_line_kernel(const KParams p) {
+__global__ void __launch_bounds__(64, line_kernel_min_ctas(sizeof(MaskT), MT, LOG, COLD, REPLAY)) mjp_line_kernel(const KParams p) {
   using MO = MaskOps<MaskT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = (MT > 0) ? MJP_FIXED_NT : (int)blockDim.x, M = (MT > 0) ? MT : p.M, K = p.K;
@@ -683,9 +680,14 @@ __global__ void __launch_bounds__(64, line_kernel_min_ctas(sizeof(MaskT), MT, LO
     // (a tick in which more than 8 machines logged is regrouped in hash-map order: general routine)
     const bool wide = MT == 0 && MO::popc(seen) > 8;
     bool grouped = !wide;
+#if MJP_EMIT_RUNNING_POINTER
     const unsigned long long *sp = g_stage;                  // (a running pointer: the row address is not recomputed per trip)
     for (int x = 0; __any_sync(fm, !wide && x < ns); ++x, ++sp) if (!wide && x < ns) {
       const unsigned long long w = *sp;
+#else
+    for (int x = 0; __any_sync(fm, !wide && x < ns); ++x) if (!wide && x < ns) {
+      const unsigned long long w = g_stage[x];
+#endif
       const unsigned act = stage_act(w), m = stage_m(w), c = log_class(act);
       const MaskT mbit = MJP_BIT(m);
       if (m != pm) { if (gdone & mbit) grouped = false; gdone |= mbit; cdone = 0u; pm = m; pc = 3u; }
@@ -730,12 +732,6 @@ __global__ void __launch_bounds__(64, line_kernel_min_ctas(sizeof(MaskT), MT, LO
       if (open0 && t0 == t0) red_add((is_s ? p.starved : p.blocked) + (size_t)i * n_inst + g, tick_clk - t0);
       *slot = open1 ? tick_clk : QNAN;
     };
-    if (COLD && MJP_FLUSH_PREFETCH) {
-      // cold layouts: :bs / :ss / :lastclk are read from the L2-resident scratch, one slot per trip of the loops below
-      for (MaskT q = warm ? pB : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; prefetch_l1(&BS(i)); }
-      for (MaskT q = warm ? pS : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int i = MO::ffs(q); q &= q - 1; prefetch_l1(&SS(i)); }
-      for (MaskT q = warm ? touched : (MaskT)0; __any_sync(fm, q != 0);) if (q) { const int b = MO::ffs(q); q &= q - 1; prefetch_l1(&LASTCLK(b)); }
-    }
     if (MT > 0) {                                             // M <= 8: both masks fit one 32-bit word
       uint32_t q = warm ? ((uint32_t)pB | ((uint32_t)pS << 16)) : 0u;
       while (__any_sync(fm, q != 0)) if (q) {

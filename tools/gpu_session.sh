@@ -37,10 +37,13 @@ if has ab_persist; then
   done > $O/${TAG}_ab_persist.log 2>&1
   cat $O/${TAG}_ab_persist.log
 fi
-if has ab_lib; then     # the shipped library against a second build of it (mjpdes_b200/csrc/ab/, see the Makefile)
+if has ab_lib; then     # the shipped library against other builds of it (mjpdes_b200/csrc/ab*/, see the Makefile);
+  # AB_REPS interleaved repetitions per (config, library): boxes differ and the first launch of a process varies
   for c in ${AB_CONFIGS:-C5_long50_slice C5_long50 C4_mixed20_stats_many C3_sweep10 C4_mixed20_scada_many example_scada C2_example}; do
-    for lib in "" mjpdes_b200/csrc/ab*/libmjpdes_b200.so; do
-      echo -n "lib=${lib:-shipped} $c: "; MJP_LIB=$lib timeout 600 python tools/profile_config.py $c 2>&1 | tail -1
+    for rep in $(seq 1 ${AB_REPS:-3}); do
+      for lib in "" mjpdes_b200/csrc/ab*/libmjpdes_b200.so; do
+        echo -n "lib=${lib:-shipped} $c: "; MJP_LIB=$lib timeout 600 python tools/profile_config.py $c 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['ms'],2), 'ms', d['events'], d.get('records',''), d['status_counts'])"
+      done
     done
   done > $O/${TAG}_ab_lib.log 2>&1
   cat $O/${TAG}_ab_lib.log
@@ -49,6 +52,9 @@ if has cliff; then
   MJP_ROTATE=0 timeout 600 python tools/cliff_probe.py > $O/${TAG}_cliff_norotate.json 2> $O/${TAG}_cliff_norotate.err; echo "cliff0 exit $?"
   timeout 600 python tools/cliff_probe.py > $O/${TAG}_cliff_rotate.json 2> $O/${TAG}_cliff_rotate.err; echo "cliff1 exit $?"
   cat $O/${TAG}_cliff_norotate.json $O/${TAG}_cliff_rotate.json
+fi
+if has ncu_models; then   # one capture per issue model bench.py reads (profiles/issue_model*.json)
+  for c in C2_example C3_sweep10 C4_mixed20_stats C4_mixed20_stats_many C4_mixed20_scada C4_mixed20_scada_many C5_long50_slice example_scada; do prof $c; done
 fi
 if has ncu_c2; then prof C2_example; fi
 if has ncu_wide; then prof C3_sweep10; prof C4_mixed20_stats_many; prof C5_long50; fi
