@@ -33,13 +33,13 @@ def main():
              ("AJ section", find("if (__any_sync(am, b_aj != 0))")), ("UP/DOWN section", find("bring-machine-up, then -down")),
              ("TOBUF section", find("// advance2buffer core.clj:285-300")), ("TOMACH section", find("// advance2machine core.clj:263-277")),
              ("record-actions section", find("record-actions core.clj:304-326, in the order")),
-             ("loop tail", find("rare: one test on the common path"))]
+             ("loop tail", find("rare: one vote on the common path"))]
     helpers = [("flush_tick", find("auto flush_tick"), find("auto start_job")),
                ("SCADA stage/emit", find("auto stage_msg"), find("// push-log for the tick that just ended")),
                ("byte get/set, params", find("auto getb"), find("double r_end[")),
                ("get_end/set_end", find("double r_end["), find("auto px =")),
                ("next_event_time", find("auto next_event_time"), find("// ---- preprocess-model")),
-               ("group minima helpers / rescan_fut", find("constexpr int GSH = sizeof(MaskT)"), find("if (fresh_start) {")),
+               ("group minima helpers / rescan_fut", find("constexpr int GSH = "), find("if (fresh_start) {")),
                ("mark_seen/toggle/type_from", find("auto mark_seen"), find("// ---- SCADA capture")),
                ("job-type draw (whole warp)", find("keep at least one drawn job type"), find("// ---- runables")),
                ("up/down generation (whole warp)", find("Pre-generate the event AFTER"), find("bring-machine-up, then -down")),
