@@ -77,13 +77,55 @@ def kernel_source_hash() -> str:
     return h.hexdigest()
 
 
+def mangled_line_kernel(demangled: str) -> str | None:
+    """'void mjp_line_kernel<unsigned int, 5, 0, 0, 0, 0, 0>(KParams)' (ncu's kernel name) -> its symbol."""
+    import re
+    m = re.search(r"mjp_line_kernel<unsigned (int|long), (\d+), (\d), (\d), (\d), (\d), (\d)>", demangled or "")
+    if not m:
+        return None
+    mask = "j" if m.group(1) == "int" else "m"
+    return (f"_ZN3mjp15mjp_line_kernelI{mask}Li{m.group(2)}E" + "".join(f"Lb{b}E" for b in m.groups()[2:]) +
+            "EEvNS_7KParamsE")
+
+
+def kernel_sass_hash(demangled: str, so: str | None = None) -> str | None:
+    """sha256 over the instruction sequence (cuobjdump -sass) of ONE event-loop kernel in the built library: what an
+    ncu capture was really taken from.  Opcodes, modifiers, predicates' sense, immediates and branch targets count;
+    register NUMBERS do not (ptxas renames registers when unrelated source lines move, same instruction stream).  A
+    source change that leaves this kernel's code as it was -- e.g. inside a branch that only other template
+    instantiations compile -- does not make its issue model stale; any change of its instruction stream does.
+    None when cuobjdump or the kernel is not available (the source hash then decides)."""
+    import re
+    sym = mangled_line_kernel(demangled)
+    so = so or os.path.join(ROOT, "mjpdes_b200", "csrc", "libmjpdes_b200.so")
+    if sym is None or not os.path.exists(so):
+        return None
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", sym, so], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                             text=True, timeout=120).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    code = []
+    for ln in out.splitlines():
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", ln)              # "/*0a10*/   IMAD.MOV.U32 R3, RZ, RZ, R5 ;  /* encoding */"
+        if m:
+            code.append(re.sub(r"\b(U?)(R|P)\d+\b", r"\1\2", m.group(1)).strip())
+    if len(code) < 100:                              # not found (cuobjdump only warns) or not a kernel
+        return None
+    return hashlib.sha256("\n".join(code).encode()).hexdigest()
+
+
 def issue_model(name: str = ""):
     p = os.path.join(ROOT, "profiles", f"issue_model{'_' + name if name else ''}.json")
     if not os.path.exists(p):
         return None
     with open(p) as fh:
         m = json.load(fh)
-    m["stale"] = m.get("kernel_source_sha256") != kernel_source_hash()
+    now = kernel_sass_hash(m.get("kernel", "")) if m.get("kernel_sass_sha256") else None
+    if now is not None:
+        m["stale"], m["stale_basis"] = m["kernel_sass_sha256"] != now, "kernel machine code"
+    else:
+        m["stale"], m["stale_basis"] = m.get("kernel_source_sha256") != kernel_source_hash(), "kernel sources"
     return m
 
 
@@ -213,7 +255,7 @@ def issue_roofline(name: str, events_per_sec_per_gpu: float, peak_gwis: float) -
     return {"bound": "issue", "achieved": ach, "peak": peak_gwis, "unit": "Gwarp-inst/s", "frac": ach / peak_gwis,
             "warp_inst_per_event": im["warp_inst_per_event"], "lane_efficiency": im.get("lane_efficiency"),
             "issue_slot_utilisation_in_capture": im.get("issue_slot_utilisation_in_capture"),
-            "stale": im["stale"], "source": im.get("source")}
+            "stale": im["stale"], "stale_basis": im["stale_basis"], "source": im.get("source")}
 
 
 def bench_configs(args, cl: Cluster, h, peak_gwis: float, hbm_gbs: float) -> dict:
@@ -484,7 +526,7 @@ def main():
                                # DRAM bytes of ONE launch of the bench configuration itself, measured by ncu
                                # (dram__bytes_read.sum + dram__bytes_write.sum); null if that capture is missing
                                "traffic": im.get("dram_bytes_per_launch_bench_config"),
-                               "stale": im["stale"],
+                               "stale": im["stale"], "stale_basis": im["stale_basis"],
                                "warp_inst_per_event": im["warp_inst_per_event"],
                                "lane_efficiency": im.get("lane_efficiency"),
                                "peak_source": "148 SMs x 4 SMSPs x clocks.max.sm (SURVEY 8d); warp-inst/event from "

@@ -22,7 +22,8 @@ def build():
         for f in ("mjp_line_kernel.cuh", "mjp_aux_kernels.cuh", "mjp_device.cuh", "mjp_params.h", "mjp_plan.h")] + [
         os.path.join(_ROOT, "include", "mjpdes_b200.h")]
     if (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB_PATH,
+        extra = os.environ.get("MJP_HOSTSIM_FLAGS", "").split()       # e.g. -DMJP_FLUSH_MERGED=1: an experiment's code path
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *extra, "-o", LIB_PATH,
                                os.path.join(_HERE, "hostsim.cpp")])
 
 

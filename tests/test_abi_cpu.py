@@ -105,3 +105,26 @@ def test_product_package_never_touches_the_oracle():
                 text = open(os.path.join(dp, fn)).read()
                 assert "mjp_oracle" not in text and "oracle." not in text and "import oracle" not in text and \
                     "hostsim" not in text, f"{fn} refers to the oracle / host shim"
+
+
+def test_issue_models_are_tied_to_the_built_kernels():
+    """bench.py's roofline reads warp-instructions per event from profiles/issue_model*.json; each file names the
+    kernel it was captured from and carries a hash of that kernel's instruction stream in the built library, so a
+    capture of other code shows as roofline.stale instead of being reused silently."""
+    import glob
+    import json
+    import shutil
+    import bench
+    assert bench.mangled_line_kernel("void mjp_line_kernel<unsigned long, 0, 0, 0, 1, 0, 1>(KParams)") == \
+        "_ZN3mjp15mjp_line_kernelImLi0ELb0ELb0ELb1ELb0ELb1EEEvNS_7KParamsE"
+    assert bench.mangled_line_kernel("something else") is None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "issue_model*.json")))
+    assert len(files) >= 8
+    for f in files:
+        d = json.load(open(f))
+        assert bench.mangled_line_kernel(d["kernel"]) and d["kernel_source_sha256"] and d["kernel_sass_sha256"]
+    if shutil.which("cuobjdump") and os.path.exists(abi.LIB_PATH):
+        m = bench.issue_model("")
+        assert m["stale_basis"] == "kernel machine code" and m["stale"] in (False, True)
+        h = bench.kernel_sass_hash(m["kernel"])
+        assert h and h == bench.kernel_sass_hash(m["kernel"])                 # deterministic

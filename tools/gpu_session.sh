@@ -16,6 +16,12 @@ if has tests_sel; then   # a subset: TESTS="tests/test_x.py -k expr"
   timeout 1200 python -m pytest $TESTS -m gpu -x -q > $O/${TAG}_tests_sel.log 2>&1; echo "tests_sel exit $?" >> $O/${TAG}_tests_sel.log
   tail -5 $O/${TAG}_tests_sel.log
 fi
+if has fuzz; then       # differential fuzz through the C ABI against the oracle: default layouts, forced cold layouts, wild profile
+  { timeout 300 python tests/fuzz/gpu_fuzz.py ${FUZZ_S:-60} ${FUZZ_FIRST:-3000000} 2>&1 | tail -2
+    MJP_COLD=1 timeout 300 python tests/fuzz/gpu_fuzz.py ${FUZZ_S:-60} $(( ${FUZZ_FIRST:-3000000} + 100000 )) 2>&1 | tail -2
+    MJP_COLD=1 timeout 300 python tests/fuzz/gpu_fuzz.py ${FUZZ_S:-60} $(( ${FUZZ_FIRST:-3000000} + 200000 )) wild 2>&1 | tail -2; } > $O/${TAG}_fuzz.log 2>&1
+  cat $O/${TAG}_fuzz.log
+fi
 if has bench; then
   timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench exit $?"
   tail -c 600 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err
@@ -56,6 +62,7 @@ fi
 if has ncu_models; then   # one capture per issue model bench.py reads (profiles/issue_model*.json)
   for c in C2_example C3_sweep10 C4_mixed20_stats C4_mixed20_stats_many C4_mixed20_scada C4_mixed20_scada_many C5_long50_slice example_scada; do prof $c; done
 fi
+if has ncu_cold; then for c in C3_sweep10 C4_mixed20_stats_many C5_long50_slice C4_mixed20_scada_many; do prof $c; done; fi
 if has ncu_c2; then prof C2_example; fi
 if has ncu_wide; then prof C3_sweep10; prof C4_mixed20_stats_many; prof C5_long50; fi
 if has ncu_c4; then prof C4_mixed20_stats; prof C4_mixed20_scada; prof C4_mixed20_scada_many; fi

@@ -54,6 +54,7 @@ def main():
         "stall_no_instruction_per_issue": num(m, "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"),
         "stall_long_scoreboard_per_issue": num(m, "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
         "kernel_source_sha256": bench.kernel_source_hash(),
+        "kernel_sass_sha256": bench.kernel_sass_hash(m["Kernel Name"][0]),      # of the built library the capture ran on
     }
     if ev.get("records"):
         out["records_in_capture"] = ev["records"]
