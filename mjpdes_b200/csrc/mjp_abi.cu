@@ -603,6 +603,8 @@ static int download_impl(mjp_handle *h, mjp_stats_out *s, mjp_log_out *log, uint
   int rc = MJP_OK;
   if (log) {
     log->count = 0; log->dropped = 0;
+    if (!h->want_log && log->first_state)             // no capture ran: "nothing printed yet" for every instance
+      std::memset(log->first_state + lo * 2 * (size_t)kp.M, 0xFF, (size_t)2 * kp.M * n * sizeof(uint32_t));
     if (h->want_log) {
       unsigned long long cur[2] = {0, 0};
       CK(cudaMemcpyAsync(cur, h->d_logcur.ptr, 16, cudaMemcpyDeviceToHost, h->stream));
