@@ -78,6 +78,17 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
   kp.resume = sl > 0;
   for (uint64_t g = 0; g < (rot ? 1 : n_inst); ++g) {
     blockIdx.x = (unsigned)g;
+#ifdef MJP_HOSTSIM_MIN
+    // the sanitizer build (asan_main.cpp) runs with the event hash on and without slicing: instantiating only those
+    // kernels cuts its compile time by an order of magnitude
+    if (!hash || sweep) return MJP_ERR_UNSUPPORTED;
+#define RUN3(MK, MT, LG) \
+    if (replay) mjp::mjp_line_kernel<MK, MT, true, true, false, LG>(kp); \
+    else mjp::mjp_line_kernel<MK, MT, false, true, false, LG>(kp);
+#define RUNC(MK, LG) \
+    if (replay) mjp::mjp_line_kernel<MK, 0, true, true, false, LG, true>(kp); \
+    else mjp::mjp_line_kernel<MK, 0, false, true, false, LG, true>(kp);
+#else
 #define RUN3(MK, MT, LG) \
     if (replay && hash && sweep) mjp::mjp_line_kernel<MK, MT, true, true, true, LG>(kp); \
     else if (replay && hash) mjp::mjp_line_kernel<MK, MT, true, true, false, LG>(kp); \
@@ -97,6 +108,7 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
     else if (hash) mjp::mjp_line_kernel<MK, 0, false, true, false, LG, true>(kp); \
     else if (sweep) mjp::mjp_line_kernel<MK, 0, false, false, true, LG, true>(kp); \
     else mjp::mjp_line_kernel<MK, 0, false, false, false, LG, true>(kp);
+#endif
     if (cold) {
       if (M > 32) { if (want_log) { RUNC(uint64_t, true) } else { RUNC(uint64_t, false) } }
       else { if (want_log) { RUNC(uint32_t, true) } else { RUNC(uint32_t, false) } }
@@ -104,7 +116,11 @@ extern "C" int hostsim_run_sliced(const mjp_line_desc *L, uint64_t n_inst, const
     else if (M > 32) { if (want_log) { RUN3(uint64_t, 0, true) } else { RUN3(uint64_t, 0, false) } }
     else switch (M) {
 #define RUNM(MT) case MT: if (want_log) { RUN3(uint32_t, MT, true) } else { RUN3(uint32_t, MT, false) } break;
+#ifdef MJP_HOSTSIM_MIN
+      RUNM(2) RUNM(5) RUNM(8)
+#else
       RUNM(2) RUNM(3) RUNM(4) RUNM(5) RUNM(6) RUNM(7) RUNM(8)
+#endif
 #undef RUNM
       default: if (want_log) { RUN3(uint32_t, 0, true) } else { RUN3(uint32_t, 0, false) } break;
     }
