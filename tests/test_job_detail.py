@@ -210,3 +210,28 @@ def test_streaming_carries_dets_from_slice_to_slice(engine, oracle):
     line.run_to = float(msgs[-1][":clk"]) + 50.0
     want = oracle.run(line, 1, mode=abi.RNG_REPLAY, seed=SEED, log_capacity=100_000, job_detail=True)
     assert [m[":dets"] for m in msgs] == literal(cm.cl, want)[:1500]
+
+
+def test_literal_snapshots_agree_with_the_messages_they_ride_on(oracle):
+    """What any correct (log/detail model) must satisfy, whatever order a tick was executed in: the snapshot is taken
+    BEFORE the action (core.clj:251,274,295-297), so a :bj / :ej of job j sees j on its machine, a :sm sees j at the
+    head of the feed buffer and nothing on the machine, an :aj sees the entry machine free, and :n is the length of
+    the buffer the job is about to enter or leave."""
+    for name, mk, n in CASES:
+        line = mk()
+        want = oracle.run(line, n, seed=SEED + 1, log_capacity=400_000, job_detail=True)
+        recs = np.sort(want.log, order=["instance", "line"])
+        assert len(recs) == len(want.dets)
+        for r, (run, bufs) in zip(recs, want.dets):
+            act, m, j, nn = int(r["act"]), int(r["machine"]), int(r["job"]), int(r["n"])
+            if act == abi.ACT_AJ:
+                assert run[0] is None
+            elif act == abi.ACT_BJ:
+                assert run[m] == j and len(bufs[m]) == nn and j not in bufs[m]
+            elif act == abi.ACT_SM:
+                assert run[m] is None and bufs[m - 1][0] == j and len(bufs[m - 1]) == nn
+            elif act == abi.ACT_EJ:
+                assert run[m] == j and m == line.M - 1
+            for b, ids in enumerate(bufs):                   # a buffer holds consecutive jobs, oldest first
+                assert ids == list(range(ids[0], ids[0] + len(ids))) if ids else True
+                assert len(ids) <= int(line.N[b])
