@@ -1,6 +1,7 @@
 #!/bin/bash
 # One gpurun session: GPU tests, bench, ncu captures.  Usage: tools/gpu_session.sh <tag> [steps...]
-# steps: tests bench ncu_c2 ncu_wide ncu_scada dram launches
+# steps: tests tests_sel(TESTS=...) fuzz bench benchq ab_lib(AB_CONFIGS=, AB_REPS=) ab_persist cliff
+#        ncu_models ncu_cold ncu_c2 ncu_wide ncu_c4 ncu_c4s ncu_slice ncu_scada dram launches
 TAG=$1; shift
 STEPS="$*"
 O=gpurun_out
